@@ -1,0 +1,91 @@
+/* mbd_b200.h — C ABI of the B200-native MBD hot path (libmbd_b200.so).
+ *
+ * The reference has no FFI layer (it is pure Python/JAX); the seams this library replaces are
+ * the Python call sites of the jitted hot path.  Each entry point cites the reference
+ * interface it stands in for.  Conventions: one host thread; every pointer marked `_dev` is
+ * device memory owned by the caller (torch tensors on the Python side); the stream is passed
+ * explicitly; return 0 on success, a negative MBD_E* code otherwise (no exceptions cross the
+ * ABI, nothing is allocated after *_create).  See INTEGRATION.md for the ctypes stub.
+ */
+#ifndef MBD_B200_H_
+#define MBD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBD_OK 0
+#define MBD_EINVAL (-1)  /* bad argument / bad blob */
+#define MBD_ECUDA (-2)   /* CUDA runtime error (see mbd_last_error) */
+#define MBD_ENOGPU (-3)  /* no CUDA device: there is deliberately NO CPU fallback */
+
+typedef struct mbd_model mbd_model;
+typedef void* mbd_stream; /* cudaStream_t */
+
+/* ABI/layout self-description (cross-checked against the Python packer in tests/test_abi.py) */
+int mbd_layout_info(int32_t* out, int n);
+const char* mbd_last_error(void);
+int mbd_device_count(void);
+
+/* brax.io.mjcf.load(...) result made device resident — replaces the `sys` captured by the
+ * jitted env.step (/root/reference/mbd/envs/humanoidrun.py:15-17).  blob: include/mbd_model.h */
+mbd_model* mbd_model_create(const uint32_t* blob_host, size_t nwords);
+void mbd_model_destroy(mbd_model*);
+
+/* eps = jax.random.normal(key,(Nsample,H,Nu)); Y0s = clip(eps*sigma + Ybar_i, -1, 1)
+ * (/root/reference/mbd/planners/mbd_planner.py:103-106) for global samples
+ * [n_begin, n_begin+n_local) of n_total.  Y0s_dev [n_local, HNu]. */
+int mbd_sample(const uint32_t key[2], int n_total, int n_begin, int n_local, int HNu, float sigma,
+               const float* Ybar_dev, float* Y0s_dev, mbd_stream s);
+
+/* jax.vmap(rollout_us, in_axes=(None,0))(state_init, Y0s)  (mbd_planner.py:109, utils.py:14-20)
+ * for a Brax-positional env (HumanoidRun.step humanoidrun.py:34-41, HumanoidTrack.step
+ * humanoidtrack.py:63-82).  state_init_dev [L,13]; Y0s_dev [n,H,Nu].
+ * Outputs (NULL = not wanted): rewss_dev [n,H]; rews_dev [n] = rewss.mean(-1) (required);
+ * logpd_dev [n] = vmap(env.eval_xref_logpd)(qs) when xref_dev [ntrack,href,3] is given;
+ * final_state_dev [n,L,13]; track_pos_dev [n,H,ntrack,3].  nsub_override>0 replaces n_frames. */
+int mbd_rollout(const mbd_model* m, const float* state_init_dev, const float* Y0s_dev, int n, int H,
+                float* rewss_dev, float* rews_dev, const float* xref_dev, int href, float* logpd_dev,
+                float* final_state_dev, float* track_pos_dev, int nsub_override, mbd_stream s);
+
+/* mbd_sample + mbd_rollout fused in ONE kernel (each CTA draws the noise of its own samples,
+ * writes Y0s once, then rolls them out): the hot path of reverse_once, mbd_planner.py:103-110. */
+int mbd_sample_rollout(const mbd_model* m, const float* state_init_dev, const uint32_t key[2], int n_total,
+                       int n_begin, int n_local, int H, float sigma, const float* Ybar_dev, float* Y0s_dev,
+                       float* rews_dev, const float* xref_dev, int href, float* logpd_dev, mbd_stream s);
+
+/* Car2d (self-contained env, /root/reference/mbd/envs/car2d.py:77-102).
+ * params_dev: [obs_center(11x2), obs_radius, dt, dt/2, dt/6]; x0_dev [3]; xref_dev [href,2] or NULL.
+ * key == NULL: Y0s_dev is an input; else it is sampled first (fused) as in mbd_sample. */
+int mbd_car2d_rollout(const float* params_dev, const float* x0_dev, const uint32_t* key, int n_total, int n_begin,
+                      int n_local, int H, float sigma, const float* Ybar_dev, float* Y0s_dev, float* rewss_dev,
+                      float* rews_dev, const float* xref_dev, int href, float* logpd_dev, float* traj_dev,
+                      mbd_stream s);
+
+/* rews.mean(), rews.std() (guard <1e-4 -> 1), logp0, demo blend, softmax
+ * (mbd_planner.py:110-127) over the GLOBAL reward vector rews_all_dev [n_total] (all ranks'
+ * samples, all-gathered by the caller); writes the softmax weights of the local slice
+ * weights_dev [n_local] and scalars_dev[4] = {rews.mean(), rew_std, max logit, sum exp}.
+ * logpd_all_dev NULL = enable_demo False.  logp_scratch_dev: n_total floats (receives logp0). */
+int mbd_softmax_weights(const float* rews_all_dev, const float* logpd_all_dev, int n_total, int n_begin,
+                        int n_local, float temp, float rew_xref, float* weights_dev, float* scalars_dev,
+                        float* logp_scratch_dev, mbd_stream s);
+
+/* partial of Ybar = einsum("n,nij->ij", weights, Y0s) over the local samples
+ * (mbd_planner.py:128), deterministic order (64-sample runs, then a pairwise tree) so that
+ * sharded and unsharded runs agree bit for bit.  scratch_dev: ceil(n_local/64)*HNu floats. */
+int mbd_weighted_sum(const float* weights_dev, const float* Y0s_dev, int n_local, int HNu, float* scratch_dev,
+                     float* partial_dev, mbd_stream s);
+
+/* Ybar = tree-sum of the P rank partials; then score / Yim1 / Ybar_im1 literally as
+ * mbd_planner.py:100,130-133.  coef = {sqrt(ab_i), 1/(1-ab_i), 1-ab_i, 1/sqrt(alpha_i), sqrt(ab_{i-1})}. */
+int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5],
+               float* Ybar_im1_dev, mbd_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBD_B200_H_ */

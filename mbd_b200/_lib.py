@@ -1,0 +1,75 @@
+"""ctypes binding of libmbd_b200.so (the C ABI in include/mbd_b200.h).
+
+The product path has NO CPU fallback: if the library is missing and cannot be built, or no
+CUDA device is present when a device entry point is called, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_vp = ctypes.c_void_p
+
+
+class MbdError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.OUT
+    if not os.path.exists(path) or _build.is_stale():
+        try:
+            path = _build.build()
+        except Exception as e:  # noqa: BLE001
+            if not os.path.exists(path):
+                raise MbdError(f"libmbd_b200.so is missing and could not be built ({e}); there is no CPU fallback") from e
+    L = ctypes.CDLL(path)
+    L.mbd_last_error.restype = ctypes.c_char_p
+    L.mbd_device_count.restype = ctypes.c_int
+    L.mbd_layout_info.argtypes = [c_i32p, ctypes.c_int]
+    L.mbd_model_create.restype = c_vp
+    L.mbd_model_create.argtypes = [c_u32p, ctypes.c_size_t]
+    L.mbd_model_destroy.argtypes = [c_vp]
+    L.mbd_sample.argtypes = [c_u32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, c_vp, c_vp, c_vp]
+    L.mbd_rollout.argtypes = [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp,
+                              ctypes.c_int, c_vp]
+    L.mbd_sample_rollout.argtypes = [c_vp, c_vp, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                     c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp]
+    L.mbd_car2d_rollout.argtypes = [c_vp, c_vp, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                    c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]
+    L.mbd_softmax_weights.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                      c_vp, c_vp, c_vp, c_vp]
+    L.mbd_weighted_sum.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]
+    L.mbd_update.argtypes = [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_f32p, c_vp, c_vp]
+    _LIB = L
+    return L
+
+
+EXPORTS = ["mbd_layout_info", "mbd_last_error", "mbd_device_count", "mbd_model_create", "mbd_model_destroy", "mbd_sample",
+           "mbd_rollout", "mbd_sample_rollout", "mbd_car2d_rollout", "mbd_softmax_weights", "mbd_weighted_sum", "mbd_update"]
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise MbdError(f"{what} failed (rc={rc}): {lib().mbd_last_error().decode()}")
+
+
+def key_ptr(key):
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    return k, k.ctypes.data_as(c_u32p)
+
+
+def require_gpu():
+    if lib().mbd_device_count() <= 0:
+        raise MbdError("no CUDA device visible: the MBD hot path has no CPU fallback")

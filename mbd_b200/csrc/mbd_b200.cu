@@ -1,0 +1,573 @@
+// mbd_b200.cu — kernels + C ABI (include/mbd_b200.h) of the B200-native MBD hot path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (see build.py).
+//
+// Kernels
+//   k_rollout<FUSED>   sampling (threefry + erfinv, optional) + Nsample x H env steps of the
+//                      Brax-positional pipeline, one link per lane, model staged by TMA.
+//   k_car2d            the self-contained kinematic car env, one sample per thread.
+//   k_sample           stand-alone jax.random.normal sampling.
+//   k_softmax_weights  global reward statistics, demo blend and softmax (single CTA).
+//   k_wsum_runs / k_wsum_tree / k_update   deterministic weighted mean + diffusion update.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mbd_b200.h"
+#include "mbd_fp32.h"
+#include "mbd_model.h"
+#include "xpbd_device.cuh"
+
+namespace mbd {
+
+constexpr int kLPS = MBD_MAXL;          // lanes per sample group
+constexpr int kRolloutThreads = 128;    // 8 sample groups per CTA
+constexpr int kSPB = kRolloutThreads / kLPS;
+constexpr int kRun = 64;                // samples per sequential run in the weighted sum
+
+// ---- TMA bulk copy of the model blob into shared memory ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void stage_model_tma(float* sblob, uint64_t* mbar, const uint32_t* gblob) {
+  constexpr uint32_t kBytes = MBD_BLOB_WORDS * 4;
+  static_assert(kBytes % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(kBytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sblob)),
+                 "l"(gblob), "r"(kBytes), "r"(smem_u32(mbar))
+                 : "memory");
+  }
+  // every thread waits for phase 0 to complete
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(mbar))
+        : "memory");
+  }
+}
+
+// ---- sampling helper: one element of clip(normal*sigma + Ybar, -1, 1) -----------------------------
+__device__ __forceinline__ float sample_elem(uint32_t k0, uint32_t k1, uint32_t idx, uint32_t total, float sigma, float ybar) {
+  float eps = mbd_bits_to_normal(mbd_random_bits_at(k0, k1, idx, total));
+  float y = eps * sigma + ybar;
+  return clampf(y, -1.0f, 1.0f);
+}
+
+__global__ void k_sample(uint32_t k0, uint32_t k1, uint32_t total, uint32_t begin, uint32_t count, int HNu, float sigma,
+                         const float* __restrict__ Ybar, float* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  uint32_t idx = begin + i;
+  out[i] = sample_elem(k0, k1, idx, total, sigma, Ybar[idx % (uint32_t)HNu]);
+}
+
+// ---- the rollout kernel ----------------------------------------------------------------------------
+struct RolloutArgs {
+  const uint32_t* blob;    // device copy of the model blob
+  const float* state_init; // [L,13]
+  float* Y0s;              // [n,H,nu]  (input, or output+input when FUSED)
+  int n, H;
+  float* rewss;            // [n,H] or null
+  float* rews;             // [n]
+  const float* xref;       // [ntrack,href,3] or null
+  int href;
+  float* logpd;            // [n] or null
+  float* final_state;      // [n,L,13] or null
+  float* track_pos;        // [n,H,ntrack,3] or null
+  int nsub_override;
+  // fused sampling
+  uint32_t k0, k1;
+  int n_total, n_begin;
+  float sigma;
+  const float* Ybar;       // [H*nu]
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
+  __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
+  __shared__ __align__(8) uint64_t mbar;
+  stage_model_tma(sblob, &mbar, a.blob);
+  ModelSmem M;
+  M.f = sblob;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int L = M.hi(MBD_H_NLINK), nu = M.hi(MBD_H_NU);
+  const int HNu = a.H * nu;
+  const int nsub = a.nsub_override > 0 ? a.nsub_override : M.hi(MBD_H_NFRAMES);
+  const int reward_kind = M.hi(MBD_H_REWARD);
+  const int ntrack = M.hi(MBD_H_NTRACK);
+
+  if (FUSED) {
+    // each CTA draws the noise of exactly its own samples, then reads it back after the barrier
+    const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+    const int first = blockIdx.x * kSPB;
+    const int cnt = min(kSPB, a.n - first) * HNu;
+    for (int e = tid; e < cnt; e += kRolloutThreads) {
+      int ns = first + e / HNu, j = e % HNu;
+      uint32_t idx = (uint32_t)(a.n_begin + ns) * (uint32_t)HNu + (uint32_t)j;
+      a.Y0s[(size_t)ns * HNu + j] = sample_elem(a.k0, a.k1, idx, total, a.sigma, a.Ybar[j]);
+    }
+    __syncthreads();
+  }
+
+  LaneCfg c;
+  load_lane_cfg(M, lane, kLPS, c);
+  StepConsts K;
+  load_step_consts(M, K);
+
+  const int n_local = blockIdx.x * kSPB + tid / kLPS;
+  const bool active = n_local < a.n;
+  const int n_rd = active ? n_local : 0;
+  const bool live = c.l < L;
+
+  LinkState s;
+  {
+    const float* st = a.state_init + (live ? c.l : 0) * MBD_STATE_STRIDE;
+    s.p = V3(st[0], st[1], st[2]);
+    s.q = Q4(st[3], st[4], st[5], st[6]);
+    s.w = V3(st[7], st[8], st[9]);
+    s.v = V3(st[10], st[11], st[12]);
+    if (!live) { s.p = V3(0, 0, 0); s.q = Q4(1, 0, 0, 0); s.w = V3(0, 0, 0); s.v = V3(0, 0, 0); }
+  }
+  // actuator.to_tau constants of this lane's dofs
+  int aid[MBD_MAXDOF];
+  float gear[MBD_MAXDOF], clo[MBD_MAXDOF], chi[MBD_MAXDOF];
+#pragma unroll
+  for (int k = 0; k < MBD_MAXDOF; ++k) {
+    int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+    bool has = live && k < c.ndof;
+    aid[k] = has ? M.li(base + MBD_D_ACT, c.l) : -1;
+    gear[k] = M.lf(base + MBD_D_GEAR, live ? c.l : 0);
+    clo[k] = M.lf(base + MBD_D_CLO, live ? c.l : 0);
+    chi[k] = M.lf(base + MBD_D_CHI, live ? c.l : 0);
+  }
+  int my_track = -1;
+  for (int k = 0; k < ntrack; ++k)
+    if (live && M.hi(MBD_H_TRACK0 + k) == c.l) my_track = k;
+
+  float rsum = 0.0f, tacc = 0.0f;
+  const float* urow = a.Y0s + (size_t)n_rd * HNu;
+  for (int t = 0; t < a.H; ++t) {
+    float tau[MBD_MAXDOF];
+#pragma unroll
+    for (int k = 0; k < MBD_MAXDOF; ++k) {
+      float u = aid[k] >= 0 ? urow[t * nu + aid[k]] : 0.0f;
+      tau[k] = aid[k] >= 0 ? gear[k] * clampf(u, clo[k], chi[k]) : 0.0f;
+    }
+    float r_pre = 0.0f;
+    if (reward_kind == MBD_REWARD_HUMANOIDTRACK && c.l == 0) {
+      v3 x0 = link_origin(M, c, s);
+      v3 v0 = link_origin_vel(M, c, s);
+      r_pre = 1.0f + ((-fabsf(v0.x - 1.6f) - fabsf(x0.z - 1.3f)) - fabsf(x0.y) * 0.1f);
+    }
+    for (int f = 0; f < nsub; ++f) positional_step(M, c, K, s, tau);
+    if (c.l == 0) {
+      float r;
+      if (reward_kind == MBD_REWARD_HUMANOIDTRACK) {
+        r = r_pre;
+      } else {
+        v3 x0 = link_origin(M, c, s);
+        if (reward_kind == MBD_REWARD_HUMANOIDRUN) {
+          float dz = clampf(fabsf(x0.z - 1.3f), -1.0f, 1.0f);
+          r = (x0.x - dz) - fabsf(x0.y) * 0.1f;
+        } else {
+          r = x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;
+        }
+      }
+      rsum += r;
+      if (a.rewss && active) a.rewss[(size_t)n_local * a.H + t] = r;
+    }
+    if (my_track >= 0) {
+      v3 x = link_origin(M, c, s);
+      if (a.track_pos && active) {
+        float* o = a.track_pos + (((size_t)n_local * a.H + t) * ntrack + my_track) * 3;
+        o[0] = x.x; o[1] = x.y; o[2] = x.z;
+      }
+      if (a.xref) {
+        int tt = t < a.href ? t : a.href - 1;
+        const float* xr = a.xref + ((size_t)my_track * a.href + tt) * 3;
+        v3 d = V3(x.x - xr[0], x.y - xr[1], x.z - xr[2]);
+        float nr = sqrtf(vdot(d, d));
+        float cl = nr < 0.5f ? nr : 0.5f;
+        float q = cl / 0.5f;
+        tacc = fmaf(q, q, tacc);
+      }
+    }
+  }
+  if (c.l == 0 && active) a.rews[n_local] = rsum / (float)a.H;
+  if (a.logpd && a.xref) {
+    // sum the per-body accumulators in track order on lane 0 of the group
+    float tot = 0.0f;
+    for (int k = 0; k < ntrack; ++k) {
+      int src = c.gbase + M.hi(MBD_H_TRACK0 + k);
+      float v = __shfl_sync(0xffffffffu, tacc, src);
+      tot += v;
+    }
+    if (c.l == 0 && active) a.logpd[n_local] = 0.0f - tot / (float)(ntrack * a.H);
+  }
+  if (a.final_state && active && live) {
+    float* o = a.final_state + ((size_t)n_local * L + c.l) * MBD_STATE_STRIDE;
+    o[0] = s.p.x; o[1] = s.p.y; o[2] = s.p.z;
+    o[3] = s.q.w; o[4] = s.q.x; o[5] = s.q.y; o[6] = s.q.z;
+    o[7] = s.w.x; o[8] = s.w.y; o[9] = s.w.z;
+    o[10] = s.v.x; o[11] = s.v.y; o[12] = s.v.z;
+  }
+}
+
+// ---- car2d (/root/reference/mbd/envs/car2d.py) ---------------------------------------------------------
+constexpr int kCarObs = 11;
+__device__ __forceinline__ void car_dynamics(const float* x, const float* u, float* o) {
+  float s, c;
+  mbd_sincosf(x[2], &s, &c);
+  o[0] = u[1] * s * 3.0f;
+  o[1] = u[1] * c * 3.0f;
+  o[2] = u[0] * 3.14159274101257324f / 3.0f * 2.0f;
+}
+struct CarArgs {
+  const float* params; const float* x0; float* Y0s; int n, H;
+  float* rewss; float* rews; const float* xref; int href; float* logpd; float* traj;
+  int fused; uint32_t k0, k1; int n_total, n_begin; float sigma; const float* Ybar;
+};
+__global__ void k_car2d(CarArgs a) {
+  __shared__ float sp[2 * kCarObs + 4];
+  if (threadIdx.x < 2 * kCarObs + 4) sp[threadIdx.x] = a.params[threadIdx.x];
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const float orad = sp[2 * kCarObs], dt = sp[2 * kCarObs + 1], hdt = sp[2 * kCarObs + 2], sdt = sp[2 * kCarObs + 3];
+  const int HNu = a.H * 2;
+  const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+  float q[3] = {a.x0[0], a.x0[1], a.x0[2]};
+  float sum = 0.0f, acc = 0.0f;
+  for (int t = 0; t < a.H; ++t) {
+    float* ur = a.Y0s + ((size_t)i * a.H + t) * 2;
+    float u0, u1;
+    if (a.fused) {
+      uint32_t idx = (uint32_t)(a.n_begin + i) * (uint32_t)HNu + (uint32_t)(2 * t);
+      u0 = sample_elem(a.k0, a.k1, idx, total, a.sigma, a.Ybar[2 * t]);
+      u1 = sample_elem(a.k0, a.k1, idx + 1, total, a.sigma, a.Ybar[2 * t + 1]);
+      ur[0] = u0; ur[1] = u1;
+    } else {
+      u0 = ur[0]; u1 = ur[1];
+    }
+    float u[2] = {clampf(u0, -1.0f, 1.0f), clampf(u1, -1.0f, 1.0f)};
+    float k1[3], k2[3], k3[3], k4[3], y[3], qn[3];
+    car_dynamics(q, u, k1);
+    for (int d = 0; d < 3; ++d) y[d] = q[d] + hdt * k1[d];
+    car_dynamics(y, u, k2);
+    for (int d = 0; d < 3; ++d) y[d] = q[d] + hdt * k2[d];
+    car_dynamics(y, u, k3);
+    for (int d = 0; d < 3; ++d) y[d] = q[d] + dt * k3[d];
+    car_dynamics(y, u, k4);
+    for (int d = 0; d < 3; ++d) qn[d] = q[d] + sdt * (((k1[d] + 2.0f * k2[d]) + 2.0f * k3[d]) + k4[d]);
+    bool collide = false;
+    for (int k = 0; k < kCarObs; ++k) {
+      float dx = qn[0] - sp[2 * k], dy = qn[1] - sp[2 * k + 1];
+      if (sqrtf(dx * dx + dy * dy) < orad) collide = true;
+    }
+    if (!collide) { q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; }
+    float dx = q[0] - 0.5f, dy = q[1] - 0.0f;
+    float d = sqrtf(dx * dx + dy * dy);
+    float cc = clampf(d, 0.0f, 0.2f) / 0.2f;
+    float r = 1.0f - cc * cc;
+    if (a.rewss) a.rewss[(size_t)i * a.H + t] = r;
+    sum += r;
+    if (a.traj) { float* o = a.traj + ((size_t)i * a.H + t) * 3; o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; }
+    if (a.xref) {
+      int tt = t < a.href ? t : a.href - 1;
+      float ex = q[0] - a.xref[2 * tt], ey = q[1] - a.xref[2 * tt + 1];
+      float dd = sqrtf(ex * ex + ey * ey);
+      float c2 = clampf(dd, 0.0f, 0.5f) / 0.5f;
+      acc += c2 * c2;
+    }
+  }
+  a.rews[i] = sum / (float)a.H;
+  if (a.logpd && a.xref) a.logpd[i] = 0.0f - acc / (float)a.H;
+}
+
+// ---- reward statistics + softmax (mbd_planner.py:110-127), single CTA ------------------------------------
+constexpr int kStatThreads = 1024;
+enum { OP_SUM = 0, OP_MAX = 1 };
+
+template <int OP>
+__device__ __forceinline__ float block_reduce(float v, float* sh) {
+  // deterministic: butterfly inside the warp, then warp 0 over the 32 warp results
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = OP == OP_SUM ? v + t : fmaxf(v, t);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[threadIdx.x & 31];
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_xor_sync(0xffffffffu, r, o);
+    r = OP == OP_SUM ? r + t : fmaxf(r, t);
+  }
+  return r;  // every thread holds the result
+}
+
+__global__ void __launch_bounds__(kStatThreads) k_softmax_weights(const float* __restrict__ rews, const float* __restrict__ logpd,
+                                                                  int N, int n_begin, int n_local, float temp, float rew_xref,
+                                                                  float* __restrict__ weights, float* __restrict__ scalars,
+                                                                  float* __restrict__ logp_scratch) {
+  __shared__ float sh[32];
+  const int tid = threadIdx.x;
+  const float fN = (float)N;
+  float acc = 0.0f;
+  for (int i = tid; i < N; i += kStatThreads) acc += rews[i];
+  const float rew_mean = block_reduce<OP_SUM>(acc, sh) / fN;
+  acc = 0.0f;
+  for (int i = tid; i < N; i += kStatThreads) { float d = rews[i] - rew_mean; acc = fmaf(d, d, acc); }
+  float rew_std = sqrtf(block_reduce<OP_SUM>(acc, sh) / fN);  // population std (ddof 0)
+  rew_std = rew_std < 1e-4f ? 1.0f : rew_std;
+  float* logp = logp_scratch;  // [N]
+  if (logpd != nullptr) {
+    float mx = -INFINITY;
+    for (int i = tid; i < N; i += kStatThreads) mx = fmaxf(mx, logpd[i]);
+    mx = block_reduce<OP_MAX>(mx, sh);
+    acc = 0.0f;
+    for (int i = tid; i < N; i += kStatThreads) {
+      float l0 = (rews[i] - rew_mean) / rew_std / temp;
+      float ld = ((logpd[i] - mx) + rew_xref - rew_mean) / rew_std / temp;
+      float l = ld > l0 ? ld : l0;
+      logp[i] = l;
+      acc += l;
+    }
+    const float lmean = block_reduce<OP_SUM>(acc, sh) / fN;
+    acc = 0.0f;
+    for (int i = tid; i < N; i += kStatThreads) { float d = logp[i] - lmean; acc = fmaf(d, d, acc); }
+    const float lstd = sqrtf(block_reduce<OP_SUM>(acc, sh) / fN);
+    for (int i = tid; i < N; i += kStatThreads) logp[i] = (logp[i] - lmean) / lstd / temp;
+  } else {
+    for (int i = tid; i < N; i += kStatThreads) logp[i] = (rews[i] - rew_mean) / rew_std / temp;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int i = tid; i < N; i += kStatThreads) mx = fmaxf(mx, logp[i]);
+  mx = block_reduce<OP_MAX>(mx, sh);
+  acc = 0.0f;
+  for (int i = tid; i < N; i += kStatThreads) acc += mbd_expf(logp[i] - mx);
+  const float S = block_reduce<OP_SUM>(acc, sh);
+  for (int i = tid; i < n_local; i += kStatThreads) weights[i] = mbd_expf(logp[n_begin + i] - mx) / S;
+  if (tid == 0) { scalars[0] = rew_mean; scalars[1] = rew_std; scalars[2] = mx; scalars[3] = S; }
+}
+
+// ---- weighted mean, deterministic order -----------------------------------------------------------------------
+// run r covers samples [r*kRun, (r+1)*kRun): out[r][j] = sum_n w[n]*Y[n][j] sequentially (fmaf)
+__global__ void k_wsum_runs(const float* __restrict__ w, const float* __restrict__ Y, int n_local, int HNu, float* __restrict__ runs) {
+  int j = blockIdx.y * blockDim.x + threadIdx.x;
+  int r = blockIdx.x;
+  if (j >= HNu) return;
+  int n0 = r * kRun, n1 = min(n0 + kRun, n_local);
+  float acc = w[n0] * Y[(size_t)n0 * HNu + j];
+  for (int n = n0 + 1; n < n1; ++n) acc = fmaf(w[n], Y[(size_t)n * HNu + j], acc);
+  runs[(size_t)r * HNu + j] = acc;
+}
+// pairwise (adjacent) tree over `count` rows of [count][HNu] -> out[HNu]; binary-counter stack
+__device__ __forceinline__ float tree_sum_rows(const float* __restrict__ rows, int count, int stride, int j) {
+  float stack[32];
+  int depth = 0;
+  for (int r = 0; r < count; ++r) {
+    float v = rows[(size_t)r * stride + j];
+    int rr = r;
+    while (rr & 1) { v = stack[--depth] + v; rr >>= 1; }
+    stack[depth++] = v;
+  }
+  // fold leftovers (count not a power of two): right-to-left
+  float v = stack[--depth];
+  while (depth > 0) v = stack[--depth] + v;
+  return v;
+}
+__global__ void k_wsum_tree(const float* __restrict__ runs, int nruns, int HNu, float* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= HNu) return;
+  out[j] = tree_sum_rows(runs, nruns, HNu, j);
+}
+__global__ void k_update(const float* __restrict__ partials, int P, int HNu, const float* __restrict__ Ybar_i, float c_sqrt_ab,
+                         float c_inv_1mab, float c_1mab, float c_inv_sqrt_a, float c_sqrt_abm1, float* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= HNu) return;
+  float Ybar = tree_sum_rows(partials, P, HNu, j);
+  // mbd_planner.py:100,130-133 literally
+  float Yi = Ybar_i[j] * c_sqrt_ab;
+  float score = c_inv_1mab * (-Yi + c_sqrt_ab * Ybar);
+  float Yim1 = c_inv_sqrt_a * (Yi + c_1mab * score);
+  out[j] = Yim1 / c_sqrt_abm1;
+}
+
+}  // namespace mbd
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+struct mbd_model {
+  uint32_t* blob_dev;
+  int L, nu, n_frames, ntrack;
+};
+
+static thread_local char g_err[256] = "";
+static int set_err(const char* where, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return MBD_ECUDA;
+}
+#define CK(call)                                  \
+  do {                                            \
+    cudaError_t e_ = (call);                      \
+    if (e_ != cudaSuccess) return set_err(#call, e_); \
+  } while (0)
+
+extern "C" {
+
+const char* mbd_last_error(void) { return g_err; }
+
+int mbd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int mbd_layout_info(int32_t* out, int n) {
+  const int32_t v[] = {(int32_t)MBD_MODEL_MAGIC, MBD_HDR_WORDS, MBD_NFIELDS, MBD_MAXL, MBD_MAXCHILD, MBD_MAXDOF, MBD_MAXCON,
+                       MBD_MAXTRACK, MBD_DOF_STRIDE, MBD_CON_STRIDE, MBD_H_DT, MBD_H_RW0, MBD_F_MASS, MBD_F_COM, MBD_F_RC,
+                       MBD_F_JQ, MBD_F_RP, MBD_F_PQ, MBD_F_PARITY, MBD_F_DOF0, MBD_F_NCON, MBD_F_CON0, MBD_BLOB_WORDS,
+                       MBD_STATE_STRIDE};
+  const int cnt = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < cnt && i < n; ++i) out[i] = v[i];
+  return cnt;
+}
+
+mbd_model* mbd_model_create(const uint32_t* blob_host, size_t nwords) {
+  if (!blob_host || nwords != MBD_BLOB_WORDS || blob_host[MBD_H_MAGIC] != MBD_MODEL_MAGIC) {
+    snprintf(g_err, sizeof(g_err), "mbd_model_create: bad blob (words=%zu)", nwords);
+    return nullptr;
+  }
+  if (mbd_device_count() <= 0) {
+    snprintf(g_err, sizeof(g_err), "mbd_model_create: no CUDA device (there is no CPU fallback)");
+    return nullptr;
+  }
+  mbd_model* m = new mbd_model();
+  const int32_t* hi = reinterpret_cast<const int32_t*>(blob_host);
+  m->L = hi[MBD_H_NLINK]; m->nu = hi[MBD_H_NU]; m->n_frames = hi[MBD_H_NFRAMES]; m->ntrack = hi[MBD_H_NTRACK];
+  if (m->L < 1 || m->L > MBD_MAXL || m->ntrack > MBD_MAXTRACK) { delete m; snprintf(g_err, sizeof(g_err), "bad link count"); return nullptr; }
+  if (cudaMalloc(&m->blob_dev, nwords * 4) != cudaSuccess || cudaMemcpy(m->blob_dev, blob_host, nwords * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "mbd_model_create: cudaMalloc/cudaMemcpy failed");
+    delete m;
+    return nullptr;
+  }
+  return m;
+}
+
+void mbd_model_destroy(mbd_model* m) {
+  if (!m) return;
+  cudaFree(m->blob_dev);
+  delete m;
+}
+
+int mbd_sample(const uint32_t key[2], int n_total, int n_begin, int n_local, int HNu, float sigma, const float* Ybar_dev,
+               float* Y0s_dev, mbd_stream s) {
+  if (!key || n_local <= 0 || HNu <= 0 || n_begin < 0 || n_begin + n_local > n_total) return MBD_EINVAL;
+  if ((uint64_t)n_total * (uint64_t)HNu >= 0xffffffffull) return MBD_EINVAL;
+  uint32_t count = (uint32_t)n_local * (uint32_t)HNu;
+  mbd::k_sample<<<(count + 255) / 256, 256, 0, (cudaStream_t)s>>>(key[0], key[1], (uint32_t)n_total * (uint32_t)HNu,
+                                                                (uint32_t)n_begin * (uint32_t)HNu, count, HNu, sigma, Ybar_dev, Y0s_dev);
+  CK(cudaGetLastError());
+  return MBD_OK;
+}
+
+static int launch_rollout(bool fused, const mbd::RolloutArgs& a, cudaStream_t st) {
+  int grid = (a.n + mbd::kSPB - 1) / mbd::kSPB;
+  if (fused)
+    mbd::k_rollout<true><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+  else
+    mbd::k_rollout<false><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+  CK(cudaGetLastError());
+  return MBD_OK;
+}
+
+int mbd_rollout(const mbd_model* m, const float* state_init_dev, const float* Y0s_dev, int n, int H, float* rewss_dev,
+                float* rews_dev, const float* xref_dev, int href, float* logpd_dev, float* final_state_dev, float* track_pos_dev,
+                int nsub_override, mbd_stream s) {
+  if (!m || !state_init_dev || !Y0s_dev || !rews_dev || n <= 0 || H <= 0) return MBD_EINVAL;
+  if (xref_dev && href <= 0) return MBD_EINVAL;
+  mbd::RolloutArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->blob_dev; a.state_init = state_init_dev; a.Y0s = const_cast<float*>(Y0s_dev); a.n = n; a.H = H;
+  a.rewss = rewss_dev; a.rews = rews_dev; a.xref = xref_dev; a.href = href; a.logpd = logpd_dev;
+  a.final_state = final_state_dev; a.track_pos = track_pos_dev; a.nsub_override = nsub_override;
+  return launch_rollout(false, a, (cudaStream_t)s);
+}
+
+int mbd_sample_rollout(const mbd_model* m, const float* state_init_dev, const uint32_t key[2], int n_total, int n_begin, int n_local,
+                       int H, float sigma, const float* Ybar_dev, float* Y0s_dev, float* rews_dev, const float* xref_dev, int href,
+                       float* logpd_dev, mbd_stream s) {
+  if (!m || !state_init_dev || !key || !Ybar_dev || !Y0s_dev || !rews_dev || n_local <= 0 || H <= 0) return MBD_EINVAL;
+  if (n_begin < 0 || n_begin + n_local > n_total) return MBD_EINVAL;
+  if ((uint64_t)n_total * (uint64_t)H * (uint64_t)m->nu >= 0xffffffffull) return MBD_EINVAL;
+  if (xref_dev && href <= 0) return MBD_EINVAL;
+  mbd::RolloutArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->blob_dev; a.state_init = state_init_dev; a.Y0s = Y0s_dev; a.n = n_local; a.H = H;
+  a.rews = rews_dev; a.xref = xref_dev; a.href = href; a.logpd = logpd_dev;
+  a.k0 = key[0]; a.k1 = key[1]; a.n_total = n_total; a.n_begin = n_begin; a.sigma = sigma; a.Ybar = Ybar_dev;
+  return launch_rollout(true, a, (cudaStream_t)s);
+}
+
+int mbd_car2d_rollout(const float* params_dev, const float* x0_dev, const uint32_t* key, int n_total, int n_begin, int n_local, int H,
+                      float sigma, const float* Ybar_dev, float* Y0s_dev, float* rewss_dev, float* rews_dev, const float* xref_dev,
+                      int href, float* logpd_dev, float* traj_dev, mbd_stream s) {
+  if (!params_dev || !x0_dev || !Y0s_dev || !rews_dev || n_local <= 0 || H <= 0) return MBD_EINVAL;
+  if (key && (!Ybar_dev || n_begin < 0 || n_begin + n_local > n_total)) return MBD_EINVAL;
+  mbd::CarArgs a;
+  memset(&a, 0, sizeof(a));
+  a.params = params_dev; a.x0 = x0_dev; a.Y0s = Y0s_dev; a.n = n_local; a.H = H; a.rewss = rewss_dev; a.rews = rews_dev;
+  a.xref = xref_dev; a.href = href; a.logpd = logpd_dev; a.traj = traj_dev;
+  a.fused = key != nullptr;
+  if (key) { a.k0 = key[0]; a.k1 = key[1]; a.n_total = n_total; a.n_begin = n_begin; a.sigma = sigma; a.Ybar = Ybar_dev; }
+  mbd::k_car2d<<<(n_local + 63) / 64, 64, 0, (cudaStream_t)s>>>(a);
+  CK(cudaGetLastError());
+  return MBD_OK;
+}
+
+int mbd_softmax_weights(const float* rews_all_dev, const float* logpd_all_dev, int n_total, int n_begin, int n_local, float temp,
+                        float rew_xref, float* weights_dev, float* scalars_dev, float* logp_scratch_dev, mbd_stream s) {
+  if (!rews_all_dev || !weights_dev || !scalars_dev || !logp_scratch_dev || n_total <= 0 || n_begin < 0 || n_begin + n_local > n_total)
+    return MBD_EINVAL;
+  mbd::k_softmax_weights<<<1, mbd::kStatThreads, 0, (cudaStream_t)s>>>(rews_all_dev, logpd_all_dev, n_total, n_begin, n_local, temp,
+                                                                    rew_xref, weights_dev, scalars_dev, logp_scratch_dev);
+  CK(cudaGetLastError());
+  return MBD_OK;
+}
+
+int mbd_weighted_sum(const float* weights_dev, const float* Y0s_dev, int n_local, int HNu, float* scratch_dev, float* partial_dev,
+                     mbd_stream s) {
+  if (!weights_dev || !Y0s_dev || !scratch_dev || !partial_dev || n_local <= 0 || HNu <= 0) return MBD_EINVAL;
+  int nruns = (n_local + mbd::kRun - 1) / mbd::kRun;
+  dim3 grid(nruns, (HNu + 255) / 256);
+  mbd::k_wsum_runs<<<grid, 256, 0, (cudaStream_t)s>>>(weights_dev, Y0s_dev, n_local, HNu, scratch_dev);
+  CK(cudaGetLastError());
+  mbd::k_wsum_tree<<<(HNu + 127) / 128, 128, 0, (cudaStream_t)s>>>(scratch_dev, nruns, HNu, partial_dev);
+  CK(cudaGetLastError());
+  return MBD_OK;
+}
+
+int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5], float* Ybar_im1_dev,
+               mbd_stream s) {
+  if (!partials_dev || !Ybar_i_dev || !coef || !Ybar_im1_dev || P <= 0 || HNu <= 0) return MBD_EINVAL;
+  mbd::k_update<<<(HNu + 127) / 128, 128, 0, (cudaStream_t)s>>>(partials_dev, P, HNu, Ybar_i_dev, coef[0], coef[1], coef[2], coef[3],
+                                                              coef[4], Ybar_im1_dev);
+  CK(cudaGetLastError());
+  return MBD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+// xpbd_device.cuh — the Brax-positional (XPBD) physics step on sm_100a, one LINK per LANE.
+//
+// Mapping: a sample group is LPS (=16) consecutive lanes of a warp; lane l of the group owns
+// link l (its COM-frame state x_i, xd_i lives in registers) and the joint that ties link l to
+// its parent.  XPBD is Jacobi-parallel over joints, so the only cross-lane traffic is
+//   * a parent-state fetch   (__shfl_sync from the parent's lane), and
+//   * a child->parent gather (each lane pulls the reaction terms of its <=4 children),
+// both inside the warp.  Model constants sit in shared memory as a field-major table
+// (include/mbd_model.h) staged by one TMA bulk copy per CTA.
+//
+// Arithmetic contract: every expression below mirrors oracle/mbd_oracle.c operation for
+// operation (same association, fmaf exactly where the oracle has fmaf; the file is compiled
+// with -fmad=false so nothing else contracts).  tests/test_rollout_gpu.py asserts BIT-EXACT
+// agreement of per-sample returns and final states.
+//
+// Reference path restated: brax.positional.pipeline.step as called from
+// /root/reference/mbd/envs/humanoidrun.py:36 (Brax itself is un-vendored: see DESIGN.md).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mbd_fp32.h"
+#include "mbd_model.h"
+
+namespace mbd {
+
+struct v3 { float x, y, z; };
+struct q4 { float w, x, y, z; };
+
+__device__ __forceinline__ v3 V3(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ q4 Q4(float w, float x, float y, float z) { q4 r; r.w = w; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ v3 vadd(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ v3 vsub(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ v3 vscale(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ v3 vfma(v3 b, float s, v3 a) { return V3(fmaf(b.x, s, a.x), fmaf(b.y, s, a.y), fmaf(b.z, s, a.z)); }
+__device__ __forceinline__ float vdot(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ v3 vcross(v3 a, v3 b) {
+  return V3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+__device__ __forceinline__ v3 vnormalize(v3 a, float* norm) {
+  float n = sqrtf(vdot(a, a));
+  float inv = (n == 0.0f) ? 0.0f : 1.0f / n;
+  *norm = n;
+  return vscale(a, inv);
+}
+__device__ __forceinline__ q4 qconj(q4 q) { return Q4(q.w, -q.x, -q.y, -q.z); }
+__device__ __forceinline__ q4 qmul(q4 u, q4 v) {
+  return Q4(fmaf(-u.z, v.z, fmaf(-u.y, v.y, fmaf(-u.x, v.x, u.w * v.w))),
+            fmaf(-u.z, v.y, fmaf(u.y, v.z, fmaf(u.x, v.w, u.w * v.x))),
+            fmaf(u.z, v.x, fmaf(u.y, v.w, fmaf(-u.x, v.z, u.w * v.y))),
+            fmaf(u.z, v.w, fmaf(-u.y, v.x, fmaf(u.x, v.y, u.w * v.z))));
+}
+__device__ __forceinline__ q4 vqmul(v3 a, q4 q) {
+  return Q4(fmaf(-a.z, q.z, fmaf(-a.y, q.y, -(a.x * q.x))),
+            fmaf(-a.z, q.y, fmaf(a.y, q.z, a.x * q.w)),
+            fmaf(a.z, q.x, fmaf(a.y, q.w, -(a.x * q.z))),
+            fmaf(a.z, q.w, fmaf(-a.y, q.x, a.x * q.y)));
+}
+__device__ __forceinline__ v3 vrotate(v3 v, q4 q) {
+  v3 u = V3(q.x, q.y, q.z);
+  v3 t = vcross(u, v);
+  t = vadd(t, t);
+  v3 c = vcross(u, t);
+  return V3(fmaf(q.w, t.x, v.x) + c.x, fmaf(q.w, t.y, v.y) + c.y, fmaf(q.w, t.z, v.z) + c.z);
+}
+__device__ __forceinline__ v3 vinv_rotate(v3 v, q4 q) { return vrotate(v, qconj(q)); }
+__device__ __forceinline__ q4 qnormalize(q4 q) {
+  float n = sqrtf(fmaf(q.z, q.z, fmaf(q.y, q.y, fmaf(q.x, q.x, q.w * q.w))));
+  float inv = 1.0f / n;
+  return Q4(q.w * inv, q.x * inv, q.y * inv, q.z * inv);
+}
+__device__ __forceinline__ q4 qadd(q4 a, q4 b) { return Q4(a.w + b.w, a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ q4 qscale(q4 a, float s) { return Q4(a.w * s, a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+__device__ __forceinline__ v3 shfl3(v3 a, int src) {
+  return V3(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src), __shfl_sync(0xffffffffu, a.z, src));
+}
+__device__ __forceinline__ q4 shfl4(q4 a, int src) {
+  return Q4(__shfl_sync(0xffffffffu, a.w, src), __shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src),
+            __shfl_sync(0xffffffffu, a.z, src));
+}
+
+// ---- shared-memory model table access ------------------------------------------------------
+struct ModelSmem {
+  const float* f;  // the blob in shared memory
+  __device__ __forceinline__ float hf(int w) const { return f[w]; }
+  __device__ __forceinline__ int hi(int w) const { return __float_as_int(f[w]); }
+  __device__ __forceinline__ float lf(int field, int l) const { return f[MBD_HDR_WORDS + field * MBD_MAXL + l]; }
+  __device__ __forceinline__ int li(int field, int l) const { return __float_as_int(lf(field, l)); }
+  __device__ __forceinline__ v3 l3(int field, int l) const { return V3(lf(field, l), lf(field + 1, l), lf(field + 2, l)); }
+  __device__ __forceinline__ q4 l4(int field, int l) const { return Q4(lf(field, l), lf(field + 1, l), lf(field + 2, l), lf(field + 3, l)); }
+};
+
+struct LinkState { v3 p; q4 q; v3 w; v3 v; };  // x_i.pos, x_i.rot, xd_i.ang, xd_i.vel
+
+struct JointAngles { float ang[3]; v3 ax[3]; float r10, r20; };
+
+// kinematics.axis_angle_ang restated — see oracle/mbd_oracle.c::axis_angle_ang
+__device__ __forceinline__ void axis_angle_ang(q4 j, float parity, JointAngles& o) {
+  float w = j.w, x = j.x, y = j.y, z = j.z;
+  float r00 = 1.0f - 2.0f * fmaf(z, z, y * y);
+  float r01 = 2.0f * fmaf(x, y, -(w * z));
+  float r02 = 2.0f * fmaf(x, z, w * y);
+  float r12 = 2.0f * fmaf(y, z, -(w * x));
+  float r22 = 1.0f - 2.0f * fmaf(y, y, x * x);
+  o.r10 = 2.0f * fmaf(x, y, w * z);
+  o.r20 = 2.0f * fmaf(x, z, -(w * y));
+  float psi = mbd_atan2f(-r12, r22);
+  float cth = sqrtf(fmaf(r01, r01, r00 * r00));
+  float theta = mbd_atan2f(r02, cth);
+  float phi = mbd_atan2f(-r01, r00);
+  float ln;
+  v3 lon = vnormalize(V3(0.0f, r22, -r12), &ln);
+  o.ang[0] = psi; o.ang[1] = theta; o.ang[2] = parity * phi;
+  o.ax[0] = V3(1.0f, 0.0f, 0.0f);
+  o.ax[1] = lon;
+  o.ax[2] = V3(parity * r02, parity * r12, parity * r22);
+}
+
+// Per-lane constants that stay in registers for the whole rollout.
+struct LaneCfg {
+  int l;         // link id (lane within the group)
+  int gbase;     // first lane of this sample group inside the warp
+  int ndof;      // -1 unused lane, 0 free root, 1..3
+  int psrc;      // warp lane of the parent (own lane when parent is the world)
+  int has_parent;
+  int csrc[MBD_MAXCHILD];  // warp lanes of the children, -1 = none
+  int ncon;
+  float inv_mass, pinv_mass, pinv_inertia, parity, ang_damp;
+  q4 pq, jq;
+  v3 rp, rc;
+};
+
+__device__ __forceinline__ void load_lane_cfg(const ModelSmem& M, int lane_in_warp, int lps, LaneCfg& c) {
+  c.l = lane_in_warp % lps;
+  c.gbase = lane_in_warp - c.l;
+  int L = M.hi(MBD_H_NLINK);
+  bool live = c.l < L && c.l < MBD_MAXL;
+  int l = live ? c.l : 0;
+  c.ndof = live ? M.li(MBD_F_NDOF, l) : -1;
+  int par = live ? M.li(MBD_F_PARENT, l) : -1;
+  c.has_parent = par >= 0;
+  c.psrc = c.gbase + (par >= 0 ? par : c.l);
+#pragma unroll
+  for (int k = 0; k < MBD_MAXCHILD; ++k) {
+    int ch = live ? M.li(MBD_F_CHILD0 + k, l) : -1;
+    c.csrc[k] = ch >= 0 ? c.gbase + ch : -1;
+  }
+  c.ncon = live ? M.li(MBD_F_NCON, l) : 0;
+  c.inv_mass = M.lf(MBD_F_INV_MASS, l);
+  c.pinv_mass = M.lf(MBD_F_PINV_MASS, l);
+  c.pinv_inertia = M.lf(MBD_F_PINV_INERTIA, l);
+  c.parity = M.lf(MBD_F_PARITY, l);
+  c.ang_damp = M.lf(MBD_F_ANG_DAMP, l);
+  c.pq = M.l4(MBD_F_PQ, l);
+  c.jq = M.l4(MBD_F_JQ, l);
+  c.rp = M.l3(MBD_F_RP, l);
+  c.rc = M.l3(MBD_F_RC, l);
+}
+
+struct StepConsts { float dt, inv_dt, half_dt, two_inv_dt, vel_damp, ang_damp, scale_pos, scale_ang, collide_scale, elasticity; v3 g; };
+
+__device__ __forceinline__ void load_step_consts(const ModelSmem& M, StepConsts& k) {
+  k.dt = M.hf(MBD_H_DT); k.inv_dt = M.hf(MBD_H_INV_DT); k.half_dt = M.hf(MBD_H_HALF_DT); k.two_inv_dt = M.hf(MBD_H_TWO_INV_DT);
+  k.vel_damp = M.hf(MBD_H_VEL_DAMP); k.ang_damp = M.hf(MBD_H_ANG_DAMP);
+  k.scale_pos = M.hf(MBD_H_SCALE_POS); k.scale_ang = M.hf(MBD_H_SCALE_ANG);
+  k.collide_scale = M.hf(MBD_H_COLLIDE_SCALE); k.elasticity = M.hf(MBD_H_ELASTICITY);
+  k.g = V3(M.hf(MBD_H_GX), M.hf(MBD_H_GY), M.hf(MBD_H_GZ));
+}
+
+// One brax.positional.pipeline.step for the link owned by this lane.  tau[k] = gear*clip(act) of
+// the lane's dof k (actuator.to_tau), already resolved by the caller.  All 32 lanes must call.
+__device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCfg& c, const StepConsts& K,
+                                                LinkState& s, const float tau[MBD_MAXDOF]) {
+  const bool jointed = c.ndof > 0;
+  const LinkState prev = s;  // x_i_prev
+
+  // ---- parent state (world = identity / zero) ----------------------------------------------
+  q4 qp = shfl4(s.q, c.psrc);
+  v3 wp = shfl3(s.w, c.psrc);
+  if (!c.has_parent) { qp = Q4(1.0f, 0.0f, 0.0f, 0.0f); wp = V3(0.0f, 0.0f, 0.0f); }
+
+  // ---- joints.acceleration_update ----------------------------------------------------------
+  v3 T = V3(0.0f, 0.0f, 0.0f);
+  if (jointed) {
+    q4 a_p = qmul(qp, c.pq);
+    q4 a_c = qmul(s.q, c.jq);
+    q4 j = qmul(qconj(a_p), a_c);
+    v3 jd = vinv_rotate(vsub(s.w, wp), a_p);
+    JointAngles ja;
+    axis_angle_ang(j, c.parity, ja);
+    v3 tq = vscale(jd, -c.ang_damp);
+#pragma unroll
+    for (int k = 0; k < MBD_MAXDOF; ++k) {
+      if (k < c.ndof) {
+        int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+        float vel = vdot(ja.ax[k], jd);
+        float t = fmaf(-M.lf(base + MBD_D_DAMP, c.l), vel, fmaf(-M.lf(base + MBD_D_STIFF, c.l), ja.ang[k], tau[k]));
+        tq = vfma(ja.ax[k], t, tq);
+      }
+    }
+    T = vrotate(tq, a_p);
+  }
+  // gather: acc = T_own - sum_children T_child (ascending child order)
+  v3 acc = T;
+#pragma unroll
+  for (int k = 0; k < MBD_MAXCHILD; ++k) {
+    int src = c.csrc[k];
+    v3 tc = shfl3(T, src >= 0 ? src : 0);
+    if (src >= 0) acc = vsub(acc, tc);
+  }
+  // ---- integrator.integrate_xdd ---------------------------------------------------------------
+  s.w = V3(fmaf(acc.x, K.dt, s.w.x * K.ang_damp), fmaf(acc.y, K.dt, s.w.y * K.ang_damp), fmaf(acc.z, K.dt, s.w.z * K.ang_damp));
+  s.v = V3(fmaf(K.g.x, K.dt, s.v.x * K.vel_damp), fmaf(K.g.y, K.dt, s.v.y * K.vel_damp), fmaf(K.g.z, K.dt, s.v.z * K.vel_damp));
+  s.q = qnormalize(qadd(s.q, vqmul(vscale(s.w, K.half_dt), s.q)));
+  s.p = vfma(s.v, K.dt, s.p);
+  const v3 w_before = s.w, v_before = s.v;  // xd_i right after integration
+
+  // ---- joints.position_update -------------------------------------------------------------------
+  v3 pp = shfl3(s.p, c.psrc);
+  qp = shfl4(s.q, c.psrc);
+  if (!c.has_parent) { pp = V3(0.0f, 0.0f, 0.0f); qp = Q4(1.0f, 0.0f, 0.0f, 0.0f); }
+  v3 dpc = V3(0.0f, 0.0f, 0.0f), dpp = V3(0.0f, 0.0f, 0.0f);
+  q4 dqc = Q4(0.0f, 0.0f, 0.0f, 0.0f), dqp = Q4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (jointed) {
+    const float im_c = c.inv_mass, im_p = c.pinv_mass, ii_p = c.pinv_inertia;
+    v3 rpw = vrotate(c.rp, qp);
+    v3 rcw = vrotate(c.rc, s.q);
+    v3 e = vsub(vadd(s.p, rcw), vadd(pp, rpw));
+    float cn;
+    v3 n = vnormalize(e, &cn);
+    v3 crc = vcross(rcw, n), crp = vcross(rpw, n);
+    float w_c = im_c + vdot(crc, crc);
+    float w_p = fmaf(ii_p, vdot(crp, crp), im_p);
+    float dl = -cn / (w_p + w_c + 1e-6f);
+    v3 P = vscale(n, dl);
+    v3 dp_c = vscale(P, im_c);
+    q4 dq_c = qscale(vqmul(vcross(rcw, P), s.q), 0.5f);
+    v3 dp_p = vscale(P, -im_p);
+    q4 dq_p = qscale(vqmul(vcross(rpw, P), qp), -0.5f * ii_p);
+    q4 a_p = qmul(qp, c.pq);
+    q4 a_c = qmul(s.q, c.jq);
+    q4 j = qmul(qconj(a_p), a_c);
+    JointAngles ja;
+    axis_angle_ang(j, c.parity, ja);
+    const int b0 = MBD_F_DOF0, b1 = MBD_F_DOF0 + MBD_DOF_STRIDE, b2 = MBD_F_DOF0 + 2 * MBD_DOF_STRIDE;
+    float e0 = ja.ang[0] - clampf(ja.ang[0], M.lf(b0 + MBD_D_LO, c.l), M.lf(b0 + MBD_D_HI, c.l));
+    float e1 = ja.ang[1] - clampf(ja.ang[1], M.lf(b1 + MBD_D_LO, c.l), M.lf(b1 + MBD_D_HI, c.l));
+    float e2 = ja.ang[2] - clampf(ja.ang[2], M.lf(b2 + MBD_D_LO, c.l), M.lf(b2 + MBD_D_HI, c.l));
+    v3 dqj_n = vscale(ja.ax[0], e0);
+    dqj_n = vfma(ja.ax[1], e1, dqj_n);
+    dqj_n = vfma(ja.ax[2], e2, dqj_n);
+    v3 dqj_1 = V3(e0, -ja.r20, ja.r10);
+    v3 dqj = (c.ndof == 1) ? dqj_1 : dqj_n;
+    v3 dq = vrotate(dqj, a_p);
+    float th;
+    v3 na = vnormalize(dq, &th);
+    float nn = vdot(na, na);
+    float dla = -th / (fmaf(ii_p, nn, nn) + 1e-6f);
+    v3 Pa = vscale(na, dla);
+    q4 dqa_c = qscale(vqmul(Pa, s.q), 0.5f);
+    q4 dqa_p = qscale(vqmul(Pa, qp), -0.5f * ii_p);
+    dpc = vscale(dp_c, K.scale_pos);
+    dpp = vscale(dp_p, K.scale_pos);
+    dqc = qadd(qscale(dq_c, K.scale_pos), qscale(dqa_c, K.scale_ang));
+    dqp = qadd(qscale(dq_p, K.scale_pos), qscale(dqa_p, K.scale_ang));
+  }
+  {
+    v3 dp = dpc;
+    q4 dq = dqc;
+#pragma unroll
+    for (int k = 0; k < MBD_MAXCHILD; ++k) {
+      int src = c.csrc[k];
+      v3 a = shfl3(dpp, src >= 0 ? src : 0);
+      q4 b = shfl4(dqp, src >= 0 ? src : 0);
+      if (src >= 0) { dp = vadd(dp, a); dq = qadd(dq, b); }
+    }
+    s.p = vadd(s.p, dp);
+    s.q = qnormalize(qadd(s.q, dq));
+  }
+  // ---- contact.get + collisions.resolve_position ---------------------------------------------------
+  float dlam[MBD_MAXCON];
+  v3 cpos[MBD_MAXCON];
+#pragma unroll
+  for (int ci = 0; ci < MBD_MAXCON; ++ci) { dlam[ci] = 0.0f; cpos[ci] = V3(0.0f, 0.0f, 0.0f); }
+  const v3 nrm = V3(0.0f, 0.0f, 1.0f);
+  if (c.ncon > 0) {
+    const float im = c.inv_mass;
+    v3 dp = V3(0.0f, 0.0f, 0.0f);
+    q4 dq = Q4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int ci = 0; ci < MBD_MAXCON; ++ci) {
+      if (ci < c.ncon) {
+        int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
+        float radius = M.lf(base + 3, c.l), mu = M.lf(base + 4, c.l);
+        v3 centre = vadd(s.p, vrotate(M.l3(base, c.l), s.q));
+        float dist = centre.z - radius;
+        v3 cp = V3(centre.x, centre.y, centre.z - (radius + 0.5f * dist));
+        cpos[ci] = cp;
+        bool coll = dist < 0.0f;
+        v3 r = vsub(cp, s.p);
+        v3 cr = vcross(r, nrm);
+        float w = im + vdot(cr, cr);
+        float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
+        v3 P = vscale(nrm, dl);
+        dp = vadd(dp, vscale(P, im));
+        dq = qadd(dq, qscale(vqmul(vcross(r, P), s.q), 0.5f));
+        v3 rl = vinv_rotate(r, s.q);
+        v3 pbar = vadd(prev.p, vrotate(rl, prev.q));
+        v3 d = vsub(cp, pbar);
+        v3 dt_ = vsub(d, vscale(nrm, vdot(d, nrm)));
+        float ct;
+        v3 nt = vnormalize(dt_, &ct);
+        v3 crt = vcross(r, nt);
+        float wt = im + vdot(crt, crt);
+        float dlt = -ct / (wt + 1e-6f);
+        bool stat = coll && (fabsf(dlt) < mu * fabsf(dl));
+        float dlt_m = stat ? dlt : 0.0f;
+        v3 Pt = vscale(nt, dlt_m);
+        dp = vadd(dp, vscale(Pt, im));
+        dq = qadd(dq, qscale(vqmul(vcross(r, Pt), s.q), 0.5f));
+        dlam[ci] = dl;
+      }
+    }
+    s.p = vfma(dp, K.collide_scale, s.p);
+    s.q = qnormalize(qadd(s.q, qscale(dq, K.collide_scale)));
+  }
+  // ---- integrator.project_xd -----------------------------------------------------------------------
+  {
+    s.v = vscale(vsub(s.p, prev.p), K.inv_dt);
+    q4 dq = qmul(s.q, qconj(prev.q));
+    float sc = dq.w >= 0.0f ? K.two_inv_dt : -K.two_inv_dt;
+    s.w = V3(dq.x * sc, dq.y * sc, dq.z * sc);
+  }
+  // ---- collisions.resolve_velocity -------------------------------------------------------------------
+  if (c.ncon > 0) {
+    const float im = c.inv_mass;
+    v3 dv = V3(0.0f, 0.0f, 0.0f), dw = V3(0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int ci = 0; ci < MBD_MAXCON; ++ci) {
+      if (ci < c.ncon) {
+        int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
+        float mu = M.lf(base + 4, c.l);
+        float dl = dlam[ci];
+        v3 r = vsub(cpos[ci], s.p);
+        v3 rel = vadd(s.v, vcross(s.w, r));
+        float vn = vdot(rel, nrm);
+        v3 vt = vsub(rel, vscale(nrm, vn));
+        float vtn;
+        v3 vtd = vnormalize(vt, &vtn);
+        float fr = mu * fabsf(dl) * K.inv_dt;
+        float mag = fr < vtn ? fr : vtn;
+        v3 dvel = vscale(vtd, -mag);
+        v3 crd = vcross(r, vtd);
+        float wd = im + vdot(crd, crd);
+        v3 p_dyn = vscale(dvel, 1.0f / (wd + 1e-6f));
+        v3 rel_old = vadd(v_before, vcross(w_before, r));
+        float vn_old = vdot(rel_old, nrm);
+        float rest = -K.elasticity * vn_old;
+        rest = rest < 0.0f ? rest : 0.0f;
+        v3 dv_rest = vscale(nrm, -vn + rest);
+        v3 crn = vcross(r, nrm);
+        float wn = im + vdot(crn, crn);
+        v3 p_rest = vscale(dv_rest, 1.0f / (wn + 1e-6f));
+        bool sinking = vn_old <= 0.0f;
+        v3 P = p_dyn;
+        if (sinking) P = vadd(P, p_rest);
+        if (dl == 0.0f) P = V3(0.0f, 0.0f, 0.0f);
+        dv = vadd(dv, vscale(P, im));
+        dw = vadd(dw, vcross(r, P));
+      }
+    }
+    s.v = vadd(s.v, dv);
+    s.w = vadd(s.w, dw);
+  }
+}
+
+// com.to_world pieces
+__device__ __forceinline__ v3 link_origin(const ModelSmem& M, const LaneCfg& c, const LinkState& s) {
+  return vsub(s.p, vrotate(M.l3(MBD_F_COM, c.l < MBD_MAXL ? c.l : 0), s.q));
+}
+__device__ __forceinline__ v3 link_origin_vel(const ModelSmem& M, const LaneCfg& c, const LinkState& s) {
+  v3 rc = vrotate(M.l3(MBD_F_COM, c.l < MBD_MAXL ? c.l : 0), s.q);
+  return vadd(s.v, vcross(rc, s.w));
+}
+
+}  // namespace mbd

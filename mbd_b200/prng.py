@@ -1,0 +1,60 @@
+"""Host-side JAX-compatible PRNG key management (threefry2x32, legacy non-partitionable layout).
+
+Mirrors what the reference gets from `jax.random.PRNGKey / split / uniform`
+(/root/reference/mbd/planners/mbd_planner.py:40,79,103,150; envs/humanoidrun.py:21-27).
+Only key bookkeeping and the 47 reset-noise uniforms run here (once per solve); the bulk
+`jax.random.normal` of `reverse_once` is generated on the GPU (csrc/mbd_kernels.cu).
+Known-answer vectors from JAX's own test-suite are checked in tests/test_prng.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def _rotl(x, r):
+    return ((x << np.uint32(r)) | (x >> np.uint32(32 - r))).astype(np.uint32)
+
+
+def threefry2x32(key, c0, c1):
+    """Vectorised threefry2x32: key uint32[2]; c0, c1 uint32 arrays -> (o0, o1)."""
+    with np.errstate(over="ignore"):
+        k0, k1 = np.uint32(key[0]), np.uint32(key[1])
+        ks = [k0, k1, np.uint32(k0 ^ k1 ^ np.uint32(0x1BD11BDA))]
+        x0 = (np.asarray(c0, dtype=np.uint32) + ks[0]).astype(np.uint32)
+        x1 = (np.asarray(c1, dtype=np.uint32) + ks[1]).astype(np.uint32)
+        for i in range(5):
+            for r in _ROT[i % 2]:
+                x0 = (x0 + x1).astype(np.uint32)
+                x1 = _rotl(x1, r) ^ x0
+            x0 = (x0 + ks[(i + 1) % 3]).astype(np.uint32)
+            x1 = (x1 + ks[(i + 2) % 3] + np.uint32(i + 1)).astype(np.uint32)
+    return x0, x1
+
+
+def random_bits(key, total: int) -> np.ndarray:
+    """jax.random.bits(key, (total,), uint32): counters iota(total) split in halves (odd -> zero pad)."""
+    half = (total + 1) // 2
+    cnt = np.arange(2 * half, dtype=np.uint32)
+    if total % 2:
+        cnt[-1] = 0
+    o0, o1 = threefry2x32(key, cnt[:half], cnt[half:])
+    return np.concatenate([o0, o1])[:total]
+
+
+def PRNGKey(seed: int) -> np.ndarray:
+    return np.array([(int(seed) >> 32) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFF], dtype=np.uint32)
+
+
+def split(key, num: int = 2) -> np.ndarray:
+    return random_bits(key, 2 * num).reshape(num, 2)
+
+
+def uniform(key, shape, minval=0.0, maxval=1.0) -> np.ndarray:
+    total = int(np.prod(shape)) if len(shape) else 1
+    bits = random_bits(key, total)
+    unit = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    lo, hi = np.float32(minval), np.float32(maxval)
+    return np.maximum(lo, unit * (hi - lo) + lo).astype(np.float32).reshape(shape)

@@ -1,0 +1,631 @@
+/* mbd_oracle.c — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of the reference hot path `reverse_once`
+ * (/root/reference/mbd/planners/mbd_planner.py:97-135) below the planner statistics:
+ *   - jax.random.normal / uniform / split              (App. C of SURVEY.md; jax/_src/prng.py)
+ *   - Car2d.step / get_reward / eval_xref_logpd        (/root/reference/mbd/envs/car2d.py:10-102)
+ *   - mbd.utils.rollout_us                             (/root/reference/mbd/utils.py:14-20)
+ *   - HumanoidRun.step/_get_reward                     (/root/reference/mbd/envs/humanoidrun.py:34-51)
+ *   - HumanoidTrack.step/_get_reward/eval_xref_logpd   (/root/reference/mbd/envs/humanoidtrack.py:63-106)
+ *   - brax PipelineEnv.pipeline_step + brax.positional.pipeline.step (call site humanoidrun.py:36)
+ *
+ * PARITY UNPINNED for the Brax part: Brax is an un-vendored, un-pinned third-party
+ * dependency of the reference (absent from /root/reference and from this image, no JAX
+ * either), and the reference ships no tests or golden vectors.  The positional step below
+ * restates Brax 0.10.x's published algorithm (brax/positional/{pipeline,joints,collisions,
+ * integrator}.py, brax/{kinematics,com,actuator,math}.py; XPBD after Mueller et al. 2020)
+ * function by function; where Brax's exact expression could not be confirmed the choice is
+ * marked [restated].  Association order / FMA placement is OURS and is fixed (see
+ * include/mbd_fp32.h) so that this oracle and the CUDA kernel agree bit for bit.
+ * car2d and the planner arithmetic are restated from in-repo reference source and ARE pinned
+ * up to libm-level differences; the PRNG is pinned by the JAX known-answer vectors in
+ * tests/test_prng.py.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  Build: oracle/Makefile (gcc -O2 -ffp-contract=off -mfma -fopenmp).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "mbd_fp32.h"
+#include "mbd_model.h"
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ================================================================================== */
+/* brax/math.py                                                                        */
+/* ================================================================================== */
+typedef struct { float x, y, z; } v3;
+typedef struct { float w, x, y, z; } q4;
+
+static inline v3 V3(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 vadd(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 vsub(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 vscale(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+static inline v3 vneg(v3 a) { return V3(-a.x, -a.y, -a.z); }
+/* a + b*s */
+static inline v3 vfma(v3 b, float s, v3 a) { return V3(fmaf(b.x, s, a.x), fmaf(b.y, s, a.y), fmaf(b.z, s, a.z)); }
+static inline float vdot(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+static inline v3 vcross(v3 a, v3 b) {
+  return V3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+/* math.normalize: x / (norm + 1e-6*(norm==0)) — a zero vector stays zero */
+static inline v3 vnormalize(v3 a, float* norm) {
+  float n = sqrtf(vdot(a, a));
+  float inv = (n == 0.0f) ? 0.0f : 1.0f / n;
+  *norm = n;
+  return vscale(a, inv);
+}
+static inline q4 Q4(float w, float x, float y, float z) { q4 r = {w, x, y, z}; return r; }
+static inline q4 qconj(q4 q) { return Q4(q.w, -q.x, -q.y, -q.z); }
+/* math.quat_mul (Hamilton) */
+static inline q4 qmul(q4 u, q4 v) {
+  return Q4(fmaf(-u.z, v.z, fmaf(-u.y, v.y, fmaf(-u.x, v.x, u.w * v.w))),
+            fmaf(-u.z, v.y, fmaf(u.y, v.z, fmaf(u.x, v.w, u.w * v.x))),
+            fmaf(u.z, v.x, fmaf(u.y, v.w, fmaf(-u.x, v.z, u.w * v.y))),
+            fmaf(u.z, v.w, fmaf(-u.y, v.x, fmaf(u.x, v.y, u.w * v.z))));
+}
+/* quat_mul(ang_to_quat(a), q) */
+static inline q4 vqmul(v3 a, q4 q) {
+  return Q4(fmaf(-a.z, q.z, fmaf(-a.y, q.y, -(a.x * q.x))),
+            fmaf(-a.z, q.y, fmaf(a.y, q.z, a.x * q.w)),
+            fmaf(a.z, q.x, fmaf(a.y, q.w, -(a.x * q.z))),
+            fmaf(a.z, q.w, fmaf(-a.y, q.x, a.x * q.y)));
+}
+/* math.rotate for unit quaternions: v + 2 s (u x v) + 2 u x (u x v)  [restated: same map as
+ * Brax's 2(u.v)u + (s^2-u.u)v + 2s(u x v) when |q| = 1] */
+static inline v3 vrotate(v3 v, q4 q) {
+  v3 u = V3(q.x, q.y, q.z);
+  v3 t = vcross(u, v);
+  t = vadd(t, t);
+  v3 c = vcross(u, t);
+  return V3(fmaf(q.w, t.x, v.x) + c.x, fmaf(q.w, t.y, v.y) + c.y, fmaf(q.w, t.z, v.z) + c.z);
+}
+static inline v3 vinv_rotate(v3 v, q4 q) { return vrotate(v, qconj(q)); }
+static inline q4 qnormalize(q4 q) {
+  float n = sqrtf(fmaf(q.z, q.z, fmaf(q.y, q.y, fmaf(q.x, q.x, q.w * q.w))));
+  float inv = 1.0f / n;
+  return Q4(q.w * inv, q.x * inv, q.y * inv, q.z * inv);
+}
+static inline q4 qadd(q4 a, q4 b) { return Q4(a.w + b.w, a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline q4 qscale(q4 a, float s) { return Q4(a.w * s, a.x * s, a.y * s, a.z * s); }
+static inline float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+/* ================================================================================== */
+/* model blob access                                                                   */
+/* ================================================================================== */
+typedef struct { v3 p; q4 q; v3 w; v3 v; } Link; /* x_i.pos, x_i.rot, xd_i.ang, xd_i.vel */
+
+typedef struct {
+  const float* f;
+  const int32_t* i;
+  int L, nu, n_frames, reward, ntrack;
+  float dt, inv_dt, half_dt, two_inv_dt, vel_damp, ang_damp, scale_pos, scale_ang, collide_scale, elasticity;
+  v3 g;
+} Model;
+
+static inline float LFf(const Model* m, int field, int l) { return m->f[MBD_HDR_WORDS + field * MBD_MAXL + l]; }
+static inline int LFi(const Model* m, int field, int l) { return m->i[MBD_HDR_WORDS + field * MBD_MAXL + l]; }
+static inline v3 LF3(const Model* m, int field, int l) { return V3(LFf(m, field, l), LFf(m, field + 1, l), LFf(m, field + 2, l)); }
+static inline q4 LF4(const Model* m, int field, int l) {
+  return Q4(LFf(m, field, l), LFf(m, field + 1, l), LFf(m, field + 2, l), LFf(m, field + 3, l));
+}
+
+static int model_open(Model* m, const uint32_t* blob) {
+  if (blob[MBD_H_MAGIC] != MBD_MODEL_MAGIC) return -1;
+  m->f = (const float*)blob;
+  m->i = (const int32_t*)blob;
+  m->L = m->i[MBD_H_NLINK]; m->nu = m->i[MBD_H_NU]; m->n_frames = m->i[MBD_H_NFRAMES];
+  m->reward = m->i[MBD_H_REWARD]; m->ntrack = m->i[MBD_H_NTRACK];
+  m->dt = m->f[MBD_H_DT]; m->inv_dt = m->f[MBD_H_INV_DT]; m->half_dt = m->f[MBD_H_HALF_DT];
+  m->two_inv_dt = m->f[MBD_H_TWO_INV_DT];
+  m->vel_damp = m->f[MBD_H_VEL_DAMP]; m->ang_damp = m->f[MBD_H_ANG_DAMP];
+  m->scale_pos = m->f[MBD_H_SCALE_POS]; m->scale_ang = m->f[MBD_H_SCALE_ANG];
+  m->collide_scale = m->f[MBD_H_COLLIDE_SCALE]; m->elasticity = m->f[MBD_H_ELASTICITY];
+  m->g = V3(m->f[MBD_H_GX], m->f[MBD_H_GY], m->f[MBD_H_GZ]);
+  return 0;
+}
+
+/* ================================================================================== */
+/* brax/kinematics.py: world_to_joint (rotational part) + axis_angle_ang               */
+/* ================================================================================== */
+typedef struct {
+  float ang[3];   /* joint angles (psi, theta, parity*phi): intrinsic x-y'-z'' about the joint-frame axes */
+  v3 ax[3];       /* instantaneous rotation axes in the PARENT joint frame (a_p) */
+  float r10, r20; /* extra entries of R(j.rot), used by the 1-dof axis alignment */
+} JointAngles;
+
+/* kinematics.axis_angle_ang [restated]: Brax builds (psi,theta,phi) from a line of nodes
+ * cross(axis_3_c, axis_1_p) with signed_angle / arccos; that is the intrinsic Euler
+ * decomposition R(j) = Rx(psi) Ry(theta) Rz(phi) in the joint frame, extracted here from the
+ * matrix entries with atan2 only (theta = atan2(sin, cos) instead of arccos(cos)*sign(sin):
+ * same angle, better conditioned near 0).  A left-handed axis triple carries parity = -1 on
+ * the third axis/angle (kinematics.link_to_joint_frame). */
+static inline void axis_angle_ang(q4 j, float parity, JointAngles* o) {
+  float w = j.w, x = j.x, y = j.y, z = j.z;
+  float r00 = 1.0f - 2.0f * fmaf(z, z, y * y);
+  float r01 = 2.0f * fmaf(x, y, -(w * z));
+  float r02 = 2.0f * fmaf(x, z, w * y);
+  float r12 = 2.0f * fmaf(y, z, -(w * x));
+  float r22 = 1.0f - 2.0f * fmaf(y, y, x * x);
+  o->r10 = 2.0f * fmaf(x, y, w * z);
+  o->r20 = 2.0f * fmaf(x, z, -(w * y));
+  float psi = mbd_atan2f(-r12, r22);
+  float cth = sqrtf(fmaf(r01, r01, r00 * r00));
+  float theta = mbd_atan2f(r02, cth);
+  float phi = mbd_atan2f(-r01, r00);
+  float ln;
+  v3 lon = vnormalize(V3(0.0f, r22, -r12), &ln);
+  o->ang[0] = psi; o->ang[1] = theta; o->ang[2] = parity * phi;
+  o->ax[0] = V3(1.0f, 0.0f, 0.0f);
+  o->ax[1] = lon;
+  o->ax[2] = V3(parity * r02, parity * r12, parity * r22);
+}
+
+/* ================================================================================== */
+/* brax/positional/pipeline.py: step                                                   */
+/* ================================================================================== */
+static void positional_step(const Model* m, Link* s, const float* act) {
+  const int L = m->L;
+  Link prev[MBD_MAXL];
+  v3 T[MBD_MAXL];
+  memcpy(prev, s, sizeof(Link) * L); /* x_i_prev = state.x_i */
+
+  /* ---- actuator.to_tau + joints.acceleration_update -------------------------------- *
+   * per jointed link, in the parent joint frame a_p:
+   *   torque = sum_k axis_k * (tau_k - stiffness_k*angle_k - damping_k*vel_k) - constraint_ang_damping * jd.ang
+   * rotated to world, +T on the child and -T on the parent; xdd.ang = inv_inertia @ T = T
+   * (spring_inertia_scale = 1 -> identity inertia), xdd.vel = gravity.                  */
+  for (int l = 0; l < L; ++l) {
+    T[l] = V3(0, 0, 0);
+    int ndof = LFi(m, MBD_F_NDOF, l);
+    if (ndof <= 0) continue;
+    int par = LFi(m, MBD_F_PARENT, l);
+    q4 qp = par >= 0 ? s[par].q : Q4(1, 0, 0, 0);
+    v3 wp = par >= 0 ? s[par].w : V3(0, 0, 0);
+    q4 a_p = qmul(qp, LF4(m, MBD_F_PQ, l));
+    q4 a_c = qmul(s[l].q, LF4(m, MBD_F_JQ, l));
+    q4 j = qmul(qconj(a_p), a_c);
+    v3 jd = vinv_rotate(vsub(s[l].w, wp), a_p);
+    JointAngles ja;
+    axis_angle_ang(j, LFf(m, MBD_F_PARITY, l), &ja);
+    v3 tq = vscale(jd, -LFf(m, MBD_F_ANG_DAMP, l));
+    for (int k = 0; k < ndof; ++k) {
+      int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+      float vel = vdot(ja.ax[k], jd);
+      float tau = 0.0f;
+      int a_id = LFi(m, base + MBD_D_ACT, l);
+      if (a_id >= 0) /* actuator.to_tau: clip(act, ctrl_range) * gear (motor: gain 1, bias 0) */
+        tau = LFf(m, base + MBD_D_GEAR, l) * clampf(act[a_id], LFf(m, base + MBD_D_CLO, l), LFf(m, base + MBD_D_CHI, l));
+      float t = fmaf(-LFf(m, base + MBD_D_DAMP, l), vel, fmaf(-LFf(m, base + MBD_D_STIFF, l), ja.ang[k], tau));
+      tq = vfma(ja.ax[k], t, tq);
+    }
+    T[l] = vrotate(tq, a_p);
+  }
+  /* ---- integrator.integrate_xdd (semi-implicit Euler) ------------------------------- */
+  Link before[MBD_MAXL]; /* xd_i right after integration = "xd_i_before" for resolve_velocity */
+  for (int l = 0; l < L; ++l) {
+    v3 acc = T[l];
+    for (int c = 0; c < MBD_MAXCHILD; ++c) {
+      int ch = LFi(m, MBD_F_CHILD0 + c, l);
+      if (ch >= 0) acc = vsub(acc, T[ch]);
+    }
+    v3 w = s[l].w, v = s[l].v;
+    w = V3(fmaf(acc.x, m->dt, w.x * m->ang_damp), fmaf(acc.y, m->dt, w.y * m->ang_damp), fmaf(acc.z, m->dt, w.z * m->ang_damp));
+    v = V3(fmaf(m->g.x, m->dt, v.x * m->vel_damp), fmaf(m->g.y, m->dt, v.y * m->vel_damp), fmaf(m->g.z, m->dt, v.z * m->vel_damp));
+    q4 q = s[l].q;
+    q = qnormalize(qadd(q, vqmul(vscale(w, m->half_dt), q)));
+    s[l].p = vfma(v, m->dt, s[l].p);
+    s[l].q = q; s[l].w = w; s[l].v = v;
+    before[l] = s[l];
+  }
+  /* ---- joints.position_update (XPBD, Jacobi over joints) ---------------------------- */
+  v3 dpc[MBD_MAXL], dpp[MBD_MAXL];
+  q4 dqc[MBD_MAXL], dqp[MBD_MAXL];
+  for (int l = 0; l < L; ++l) {
+    dpc[l] = dpp[l] = V3(0, 0, 0);
+    dqc[l] = dqp[l] = Q4(0, 0, 0, 0);
+    int ndof = LFi(m, MBD_F_NDOF, l);
+    if (ndof <= 0) continue;
+    int par = LFi(m, MBD_F_PARENT, l);
+    v3 pp = par >= 0 ? s[par].p : V3(0, 0, 0);
+    q4 qp = par >= 0 ? s[par].q : Q4(1, 0, 0, 0);
+    float im_c = LFf(m, MBD_F_INV_MASS, l), im_p = LFf(m, MBD_F_PINV_MASS, l), ii_p = LFf(m, MBD_F_PINV_INERTIA, l);
+    /* translation: pull the child anchor a_c.pos onto the parent anchor a_p.pos */
+    v3 rpw = vrotate(LF3(m, MBD_F_RP, l), qp);
+    v3 rcw = vrotate(LF3(m, MBD_F_RC, l), s[l].q);
+    v3 e = vsub(vadd(s[l].p, rcw), vadd(pp, rpw));
+    float c;
+    v3 n = vnormalize(e, &c);
+    v3 crc = vcross(rcw, n), crp = vcross(rpw, n);
+    float w_c = im_c + vdot(crc, crc);
+    float w_p = fmaf(ii_p, vdot(crp, crp), im_p);
+    float dl = -c / (w_p + w_c + 1e-6f);
+    v3 P = vscale(n, dl);
+    v3 dp_c = vscale(P, im_c);
+    q4 dq_c = qscale(vqmul(vcross(rcw, P), s[l].q), 0.5f);
+    v3 dp_p = vscale(P, -im_p);
+    q4 dq_p = qscale(vqmul(vcross(rpw, P), qp), -0.5f * ii_p);
+    /* rotation: hinge axis alignment (1 dof) / zero the missing Euler angle (2 dof) + limits */
+    q4 a_p = qmul(qp, LF4(m, MBD_F_PQ, l));
+    q4 a_c = qmul(s[l].q, LF4(m, MBD_F_JQ, l));
+    q4 j = qmul(qconj(a_p), a_c);
+    JointAngles ja;
+    axis_angle_ang(j, LFf(m, MBD_F_PARITY, l), &ja);
+    v3 dqj;
+    {
+      int b0 = MBD_F_DOF0;
+      float e0 = ja.ang[0] - clampf(ja.ang[0], LFf(m, b0 + MBD_D_LO, l), LFf(m, b0 + MBD_D_HI, l));
+      if (ndof == 1) {
+        /* dq = cross(axis_p, axis_c) + axis * (angle - clip(angle)); in the a_p frame axis_p = e_x,
+         * axis_c = first column of R(j): cross = (0, -r20, r10) */
+        dqj = V3(e0, -ja.r20, ja.r10);
+      } else {
+        int b1 = MBD_F_DOF0 + MBD_DOF_STRIDE, b2 = MBD_F_DOF0 + 2 * MBD_DOF_STRIDE;
+        float e1 = ja.ang[1] - clampf(ja.ang[1], LFf(m, b1 + MBD_D_LO, l), LFf(m, b1 + MBD_D_HI, l));
+        float e2 = ja.ang[2] - clampf(ja.ang[2], LFf(m, b2 + MBD_D_LO, l), LFf(m, b2 + MBD_D_HI, l));
+        dqj = vscale(ja.ax[0], e0);
+        dqj = vfma(ja.ax[1], e1, dqj);
+        dqj = vfma(ja.ax[2], e2, dqj);
+      }
+    }
+    v3 dq = vrotate(dqj, a_p);
+    float th;
+    v3 na = vnormalize(dq, &th);
+    float nn = vdot(na, na);
+    float dla = -th / (fmaf(ii_p, nn, nn) + 1e-6f);
+    v3 Pa = vscale(na, dla);
+    q4 dqa_c = qscale(vqmul(Pa, s[l].q), 0.5f);
+    q4 dqa_p = qscale(vqmul(Pa, qp), -0.5f * ii_p);
+    dpc[l] = vscale(dp_c, m->scale_pos);
+    dpp[l] = vscale(dp_p, m->scale_pos);
+    dqc[l] = qadd(qscale(dq_c, m->scale_pos), qscale(dqa_c, m->scale_ang));
+    dqp[l] = qadd(qscale(dq_p, m->scale_pos), qscale(dqa_p, m->scale_ang));
+  }
+  for (int l = 0; l < L; ++l) {
+    v3 dp = dpc[l];
+    q4 dq = dqc[l];
+    for (int c = 0; c < MBD_MAXCHILD; ++c) {
+      int ch = LFi(m, MBD_F_CHILD0 + c, l);
+      if (ch >= 0) { dp = vadd(dp, dpp[ch]); dq = qadd(dq, dqp[ch]); }
+    }
+    s[l].p = vadd(s[l].p, dp);
+    s[l].q = qnormalize(qadd(s[l].q, dq));
+  }
+  /* ---- contact.get (sphere-plane, MJX plane_sphere) + collisions.resolve_position ---- */
+  float dlam[MBD_MAXL][MBD_MAXCON];
+  v3 cpos[MBD_MAXL][MBD_MAXCON];
+  const v3 nrm = V3(0.0f, 0.0f, 1.0f);
+  for (int l = 0; l < L; ++l) {
+    int ncon = LFi(m, MBD_F_NCON, l);
+    if (ncon <= 0) continue;
+    float im = LFf(m, MBD_F_INV_MASS, l);
+    v3 dp = V3(0, 0, 0);
+    q4 dq = Q4(0, 0, 0, 0);
+    for (int ci = 0; ci < ncon; ++ci) {
+      int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
+      float radius = LFf(m, base + 3, l), mu = LFf(m, base + 4, l);
+      v3 centre = vadd(s[l].p, vrotate(LF3(m, base, l), s[l].q));
+      float dist = centre.z - radius;
+      v3 cp = V3(centre.x, centre.y, centre.z - (radius + 0.5f * dist)); /* pos = c - n (r + dist/2) */
+      cpos[l][ci] = cp;
+      int coll = dist < 0.0f;
+      v3 r = vsub(cp, s[l].p);
+      v3 cr = vcross(r, nrm);
+      float w = im + vdot(cr, cr);
+      float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
+      v3 P = vscale(nrm, dl);
+      dp = vadd(dp, vscale(P, im));
+      dq = qadd(dq, qscale(vqmul(vcross(r, P), s[l].q), 0.5f));
+      /* static friction: cancel the tangential travel of the contact point since x_i_prev */
+      v3 rl = vinv_rotate(r, s[l].q);
+      v3 pbar = vadd(prev[l].p, vrotate(rl, prev[l].q));
+      v3 d = vsub(cp, pbar);
+      v3 dt_ = vsub(d, vscale(nrm, vdot(d, nrm)));
+      float ct;
+      v3 nt = vnormalize(dt_, &ct);
+      v3 crt = vcross(r, nt);
+      float wt = im + vdot(crt, crt);
+      float dlt = -ct / (wt + 1e-6f);
+      int stat = coll && (fabsf(dlt) < mu * fabsf(dl));
+      float dlt_m = stat ? dlt : 0.0f;
+      v3 Pt = vscale(nt, dlt_m);
+      dp = vadd(dp, vscale(Pt, im));
+      dq = qadd(dq, qscale(vqmul(vcross(r, Pt), s[l].q), 0.5f));
+      dlam[l][ci] = dl;
+    }
+    s[l].p = vfma(dp, m->collide_scale, s[l].p);
+    s[l].q = qnormalize(qadd(s[l].q, qscale(dq, m->collide_scale)));
+  }
+  /* ---- integrator.project_xd ---------------------------------------------------------- */
+  for (int l = 0; l < L; ++l) {
+    s[l].v = vscale(vsub(s[l].p, prev[l].p), m->inv_dt);
+    q4 dq = qmul(s[l].q, qconj(prev[l].q)); /* math.relative_quat(prev, cur) */
+    float sc = dq.w >= 0.0f ? m->two_inv_dt : -m->two_inv_dt;
+    s[l].w = V3(dq.x * sc, dq.y * sc, dq.z * sc);
+  }
+  /* ---- collisions.resolve_velocity ------------------------------------------------------ */
+  for (int l = 0; l < L; ++l) {
+    int ncon = LFi(m, MBD_F_NCON, l);
+    if (ncon <= 0) continue;
+    float im = LFf(m, MBD_F_INV_MASS, l);
+    v3 dv = V3(0, 0, 0), dw = V3(0, 0, 0);
+    for (int ci = 0; ci < ncon; ++ci) {
+      int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
+      float mu = LFf(m, base + 4, l);
+      float dl = dlam[l][ci];
+      v3 r = vsub(cpos[l][ci], s[l].p);
+      v3 rel = vadd(s[l].v, vcross(s[l].w, r));
+      float vn = vdot(rel, nrm);
+      v3 vt = vsub(rel, vscale(nrm, vn));
+      float vtn;
+      v3 vtd = vnormalize(vt, &vtn);
+      float fr = mu * fabsf(dl) * m->inv_dt;
+      float mag = fr < vtn ? fr : vtn;
+      v3 dvel = vscale(vtd, -mag);
+      v3 crd = vcross(r, vtd);
+      float wd = im + vdot(crd, crd);
+      v3 p_dyn = vscale(dvel, 1.0f / (wd + 1e-6f));
+      v3 rel_old = vadd(before[l].v, vcross(before[l].w, r));
+      float vn_old = vdot(rel_old, nrm);
+      float rest = -m->elasticity * vn_old;
+      rest = rest < 0.0f ? rest : 0.0f;
+      v3 dv_rest = vscale(nrm, -vn + rest);
+      v3 crn = vcross(r, nrm);
+      float wn = im + vdot(crn, crn);
+      v3 p_rest = vscale(dv_rest, 1.0f / (wn + 1e-6f));
+      int sinking = vn_old <= 0.0f;
+      v3 P = p_dyn;
+      if (sinking) P = vadd(P, p_rest);
+      if (dl == 0.0f) P = V3(0, 0, 0);
+      dv = vadd(dv, vscale(P, im));
+      dw = vadd(dw, vcross(r, P));
+    }
+    s[l].v = vadd(s[l].v, dv);
+    s[l].w = vadd(s[l].w, dw);
+  }
+}
+
+/* com.to_world: x.pos = x_i.pos - rotate(com, rot); xd.vel = xd_i.vel + cross(rotate(com,rot), ang) */
+static inline v3 link_origin(const Model* m, const Link* s, int l) {
+  return vsub(s[l].p, vrotate(LF3(m, MBD_F_COM, l), s[l].q));
+}
+static inline v3 link_origin_vel(const Model* m, const Link* s, int l) {
+  v3 rc = vrotate(LF3(m, MBD_F_COM, l), s[l].q);
+  return vadd(s[l].v, vcross(rc, s[l].w));
+}
+
+static float reward_post(const Model* m, const Link* s) {
+  v3 x0 = link_origin(m, s, 0);
+  if (m->reward == MBD_REWARD_HUMANOIDRUN) {
+    /* humanoidrun.py:46-51 */
+    float dz = clampf(fabsf(x0.z - 1.3f), -1.0f, 1.0f);
+    return (x0.x - dz) - fabsf(x0.y) * 0.1f;
+  }
+  if (m->reward == MBD_REWARD_HOPPER) {
+    /* hopper.py:57-65 */
+    return x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;
+  }
+  return 0.0f;
+}
+static float reward_pre(const Model* m, const Link* s) {
+  /* humanoidtrack.py:87-96 — evaluated on the state BEFORE the step */
+  v3 x0 = link_origin(m, s, 0);
+  v3 v0 = link_origin_vel(m, s, 0);
+  return 1.0f + ((-fabsf(v0.x - 1.6f) - fabsf(x0.z - 1.3f)) - fabsf(x0.y) * 0.1f);
+}
+
+static void load_state(Link* s, const float* st, int L) {
+  for (int l = 0; l < L; ++l) {
+    const float* a = st + l * MBD_STATE_STRIDE;
+    s[l].p = V3(a[0], a[1], a[2]); s[l].q = Q4(a[3], a[4], a[5], a[6]);
+    s[l].w = V3(a[7], a[8], a[9]); s[l].v = V3(a[10], a[11], a[12]);
+  }
+}
+static void store_state(const Link* s, float* st, int L) {
+  for (int l = 0; l < L; ++l) {
+    float* a = st + l * MBD_STATE_STRIDE;
+    a[0] = s[l].p.x; a[1] = s[l].p.y; a[2] = s[l].p.z;
+    a[3] = s[l].q.w; a[4] = s[l].q.x; a[5] = s[l].q.y; a[6] = s[l].q.z;
+    a[7] = s[l].w.x; a[8] = s[l].w.y; a[9] = s[l].w.z;
+    a[10] = s[l].v.x; a[11] = s[l].v.y; a[12] = s[l].v.z;
+  }
+}
+
+/* vmap(rollout_us)(state_init, Y0s) — mbd_planner.py:109, utils.py:14-20.
+ * state_init [L,13] shared by all samples; Y0s [n,H,nu]; outputs:
+ *   rewss [n,H] (may be NULL), rews [n] = rewss.mean(-1), logpd [n] (NULL unless xref given),
+ *   final_state [n,L,13] (may be NULL), track_pos [n,H,ntrack,3] (may be NULL).
+ * xref [ntrack, href, 3].  nsub_override > 0 replaces n_frames (per-substep parity tests). */
+ORC_API int orc_xpbd_rollout(const uint32_t* blob, const float* state_init, const float* Y0s, int n, int H,
+                             float* rewss, float* rews, const float* xref, int href, float* logpd,
+                             float* final_state, float* track_pos, int nsub_override, int nthreads) {
+  Model m;
+  if (model_open(&m, blob)) return -1;
+  const int L = m.L, nu = m.nu;
+  const int nsub = nsub_override > 0 ? nsub_override : m.n_frames;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    Link s[MBD_MAXL];
+    load_state(s, state_init, L);
+    float sum = 0.0f;
+    float acc_k[MBD_MAXTRACK];
+    for (int k = 0; k < MBD_MAXTRACK; ++k) acc_k[k] = 0.0f;
+    for (int t = 0; t < H; ++t) {
+      const float* u = Y0s + ((size_t)i * H + t) * nu;
+      float r_pre = (m.reward == MBD_REWARD_HUMANOIDTRACK) ? reward_pre(&m, s) : 0.0f;
+      for (int f = 0; f < nsub; ++f) positional_step(&m, s, u); /* PipelineEnv.pipeline_step */
+      float r = (m.reward == MBD_REWARD_HUMANOIDTRACK) ? r_pre : reward_post(&m, s);
+      if (rewss) rewss[(size_t)i * H + t] = r;
+      sum += r;
+      for (int k = 0; k < m.ntrack; ++k) {
+        v3 x = link_origin(&m, s, m.i[MBD_H_TRACK0 + k]);
+        if (track_pos) {
+          float* o = track_pos + (((size_t)i * H + t) * m.ntrack + k) * 3;
+          o[0] = x.x; o[1] = x.y; o[2] = x.z;
+        }
+        if (xref) {
+          /* humanoidtrack.py:98-106: ((clip(|xs - xref|, 0, .5)/.5)^2).mean(); t >= href clamps
+           * to the last reference row (extension, not reference behaviour: SURVEY F9) */
+          int tt = t < href ? t : href - 1;
+          const float* xr = xref + ((size_t)k * href + tt) * 3;
+          v3 d = V3(x.x - xr[0], x.y - xr[1], x.z - xr[2]);
+          float nr = sqrtf(vdot(d, d));
+          float cl = nr < 0.5f ? nr : 0.5f;
+          float q = cl / 0.5f;
+          acc_k[k] = fmaf(q, q, acc_k[k]);
+        }
+      }
+    }
+    rews[i] = sum / (float)H;
+    if (logpd && xref) {
+      float tot = 0.0f;
+      for (int k = 0; k < m.ntrack; ++k) tot += acc_k[k];
+      logpd[i] = 0.0f - tot / (float)(m.ntrack * H);
+    }
+    if (final_state) store_state(s, final_state + (size_t)i * L * MBD_STATE_STRIDE, L);
+  }
+  return 0;
+}
+
+/* ================================================================================== */
+/* car2d (/root/reference/mbd/envs/car2d.py)                                           */
+/* ================================================================================== */
+#define CAR_NOBS 11
+static inline void car_dynamics(const float* x, const float* u, float* o) { /* car2d.py:10-19 */
+  float s, c;
+  mbd_sincosf(x[2], &s, &c);
+  o[0] = u[1] * s * 3.0f;
+  o[1] = u[1] * c * 3.0f;
+  o[2] = u[0] * 3.14159274101257324f / 3.0f * 2.0f;
+}
+static inline void car_rk4(const float* x, const float* u, float dt, float hdt, float sdt, float* xn) { /* car2d.py:22-27 */
+  float k1[3], k2[3], k3[3], k4[3], y[3]; /* hdt = f32(dt/2), sdt = f32(dt/6): Python-double constants */
+  car_dynamics(x, u, k1);
+  for (int i = 0; i < 3; ++i) y[i] = x[i] + hdt * k1[i];
+  car_dynamics(y, u, k2);
+  for (int i = 0; i < 3; ++i) y[i] = x[i] + hdt * k2[i];
+  car_dynamics(y, u, k3);
+  for (int i = 0; i < 3; ++i) y[i] = x[i] + dt * k3[i];
+  car_dynamics(y, u, k4);
+  for (int i = 0; i < 3; ++i) xn[i] = x[i] + sdt * (((k1[i] + 2.0f * k2[i]) + 2.0f * k3[i]) + k4[i]);
+}
+static inline float car_reward(const float* q) { /* car2d.py:88-93 */
+  float dx = q[0] - 0.5f, dy = q[1] - 0.0f;
+  float d = sqrtf(dx * dx + dy * dy);
+  float c = clampf(d, 0.0f, 0.2f) / 0.2f;
+  return 1.0f - c * c;
+}
+/* params: [obs_center (11x2), obs_radius, dt, dt/2, dt/6]; x0[3]; Y0s [n,H,2]; xref [href,2] or NULL */
+ORC_API int orc_car2d_rollout(const float* params, const float* x0, const float* Y0s, int n, int H,
+                              float* rewss, float* rews, const float* xref, int href, float* logpd,
+                              float* traj, int nthreads) {
+  const float* oc = params;
+  const float orad = params[2 * CAR_NOBS], dt = params[2 * CAR_NOBS + 1];
+  const float hdt = params[2 * CAR_NOBS + 2], sdt = params[2 * CAR_NOBS + 3];
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    float q[3] = {x0[0], x0[1], x0[2]};
+    float sum = 0.0f, acc = 0.0f;
+    for (int t = 0; t < H; ++t) {
+      const float* ur = Y0s + ((size_t)i * H + t) * 2;
+      float u[2] = {clampf(ur[0], -1.0f, 1.0f), clampf(ur[1], -1.0f, 1.0f)}; /* car2d.py:80 */
+      float qn[3];
+      car_rk4(q, u, dt, hdt, sdt, qn);
+      int collide = 0; /* car2d.py:30-32 */
+      for (int k = 0; k < CAR_NOBS; ++k) {
+        float dx = qn[0] - oc[2 * k], dy = qn[1] - oc[2 * k + 1];
+        if (sqrtf(dx * dx + dy * dy) < orad) collide = 1;
+      }
+      if (!collide) { q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; }
+      float r = car_reward(q);
+      if (rewss) rewss[(size_t)i * H + t] = r;
+      sum += r;
+      if (traj) { float* o = traj + ((size_t)i * H + t) * 3; o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; }
+      if (xref) { /* car2d.py:95-102 */
+        int tt = t < href ? t : href - 1;
+        float ex = q[0] - xref[2 * tt], ey = q[1] - xref[2 * tt + 1];
+        float d = sqrtf(ex * ex + ey * ey);
+        float c = clampf(d, 0.0f, 0.5f) / 0.5f;
+        acc += c * c;
+      }
+    }
+    rews[i] = sum / (float)H;
+    if (logpd && xref) logpd[i] = 0.0f - acc / (float)H;
+  }
+  return 0;
+}
+
+/* ================================================================================== */
+/* JAX PRNG                                                                            */
+/* ================================================================================== */
+ORC_API void orc_threefry2x32(const uint32_t* key, const uint32_t* ctr, uint32_t* out) {
+  mbd_threefry2x32(key[0], key[1], ctr[0], ctr[1], &out[0], &out[1]);
+}
+/* jax.random.bits(key, (total,)) */
+ORC_API void orc_random_bits(const uint32_t* key, uint32_t total, uint32_t* out) {
+  for (uint32_t i = 0; i < total; ++i) out[i] = mbd_random_bits_at(key[0], key[1], i, total);
+}
+/* jax.random.normal(key, shape) flattened; [begin, end) of `total` elements */
+ORC_API void orc_normal(const uint32_t* key, uint32_t total, uint32_t begin, uint32_t end, float* out, int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+  for (int64_t i = begin; i < (int64_t)end; ++i)
+    out[i - begin] = mbd_bits_to_normal(mbd_random_bits_at(key[0], key[1], (uint32_t)i, total));
+}
+/* reverse_once sampling, mbd_planner.py:103-106: clip(eps*sigma + Ybar, -1, 1); Ybar [H*nu] */
+ORC_API void orc_sample_Y0s(const uint32_t* key, int n_total, int n_begin, int n_end, int HNu, float sigma,
+                            const float* Ybar, float* out, int nthreads) {
+  const uint32_t total = (uint32_t)n_total * (uint32_t)HNu;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+  for (int i = n_begin; i < n_end; ++i)
+    for (int e = 0; e < HNu; ++e) {
+      uint32_t idx = (uint32_t)i * (uint32_t)HNu + (uint32_t)e;
+      float eps = mbd_bits_to_normal(mbd_random_bits_at(key[0], key[1], idx, total));
+      float y = eps * sigma + Ybar[e];
+      out[(size_t)(i - n_begin) * HNu + e] = clampf(y, -1.0f, 1.0f);
+    }
+}
+
+/* scalar math spec, exported so tests can check accuracy against float64 */
+ORC_API float orc_atan2f(float y, float x) { return mbd_atan2f(y, x); }
+ORC_API float orc_sinf(float x) { return mbd_sinf(x); }
+ORC_API float orc_cosf(float x) { return mbd_cosf(x); }
+ORC_API float orc_logf(float x) { return mbd_logf(x); }
+ORC_API float orc_expf(float x) { return mbd_expf(x); }
+ORC_API float orc_erfinvf(float x) { return mbd_erfinvf(x); }
+ORC_API void orc_map(int fn, const float* a, const float* b, float* out, int n) {
+  for (int i = 0; i < n; ++i) {
+    switch (fn) {
+      case 0: out[i] = mbd_atan2f(a[i], b[i]); break;
+      case 1: out[i] = mbd_sinf(a[i]); break;
+      case 2: out[i] = mbd_cosf(a[i]); break;
+      case 3: out[i] = mbd_logf(a[i]); break;
+      case 4: out[i] = mbd_expf(a[i]); break;
+      case 5: out[i] = mbd_erfinvf(a[i]); break;
+    }
+  }
+}
+ORC_API int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
