@@ -37,17 +37,20 @@ def forward(sys: System, q: np.ndarray, qd: np.ndarray):
             xang[l] = qd[ds + 3:ds + 6]
             continue
         nd = int(sys.link_types[l])
-        if np.any(sys.dof_is_slide[ds:ds + nd]):
-            raise NotImplementedError("slide joints")
         # stacked hinges: j.rot = r0*r1*r2; jd.ang = w0 + R(r0) w1 + R(r0 r1) w2 (link-transform frame)
         jrot = np.array([1.0, 0, 0, 0])
         jang = np.zeros(3)
+        slide_pos, slide_vel = np.zeros(3), np.zeros(3)
         for k in range(nd):
             axis = sys.dof_axis[ds + k]
+            if sys.dof_is_slide[ds + k]:  # prismatic dof: translation along the axis (link-transform frame)
+                slide_pos = slide_pos + rotate(axis * q[qs + k], jrot)
+                slide_vel = slide_vel + rotate(axis * qd[ds + k], jrot)
+                continue
             jang = jang + rotate(axis * qd[ds + k], jrot)
             jrot = quat_mul(jrot, _quat_rot_axis(axis, q[qs + k]))
         jp = sys.joint_pos[l]
-        jpos = jp - rotate(jp, jrot)  # rotation about the joint anchor
+        jpos = jp - rotate(jp, jrot) + slide_pos  # rotation about the joint anchor (+ slide offset)
         ppos = xpos[par] if par >= 0 else np.zeros(3)
         prot = xrot[par] if par >= 0 else np.array([1.0, 0, 0, 0])
         pang = xang[par] if par >= 0 else np.zeros(3)
@@ -60,7 +63,7 @@ def forward(sys: System, q: np.ndarray, qd: np.ndarray):
         w_rel = rotate(jang, trot)
         xang[l] = pang + w_rel
         anchor = xpos[l] + rotate(jp, xrot[l])
-        xvel[l] = pvel + np.cross(pang, xpos[l] - ppos) + np.cross(w_rel, xpos[l] - anchor)
+        xvel[l] = pvel + np.cross(pang, xpos[l] - ppos) + np.cross(w_rel, xpos[l] - anchor) + rotate(slide_vel, trot)
     return xpos, xrot, xang, xvel
 
 
@@ -89,3 +92,39 @@ def to_world(sys: System, state: np.ndarray, links=None):
         pos[i] = st[i, 0:3] - rc
         vel[i] = st[i, 10:13] + np.cross(rc, st[i, 7:10])
     return pos, st[:, 3:7].copy(), st[:, 7:10].copy(), vel
+
+
+def inverse(sys: System, xpos, xrot, xang, xvel, links=None):
+    """kinematics.inverse (restated): joint coordinates (q, qd) from world link transforms.
+    Hinge angles are the intrinsic x-y'-z'' Euler angles of the joint-frame relative rotation,
+    rates are the projections of the relative angular velocity on the instantaneous axes —
+    the same quantities the physics step uses (axis_angle_ang)."""
+    links = list(range(sys.num_links())) if links is None else list(links)
+    q = np.array(sys.init_q, dtype=np.float64).copy()
+    qd = np.zeros(sys.qd_size())
+    for l in links:
+        qs, ds = int(sys.link_q_start[l]), int(sys.link_dof_start[l])
+        if sys.link_types[l] == "f":
+            q[qs:qs + 3], q[qs + 3:qs + 7] = xpos[l], xrot[l]
+            qd[ds:ds + 3], qd[ds + 3:ds + 6] = xvel[l], xang[l]
+            continue
+        nd = int(sys.link_types[l])
+        par = sys.link_parents[l]
+        prot = xrot[par] if par >= 0 else np.array([1.0, 0, 0, 0])
+        pang = xang[par] if par >= 0 else np.zeros(3)
+        a_p = quat_mul(quat_mul(prot, sys.link_rot[l]), sys.joint_rot[l])
+        a_c = quat_mul(xrot[l], sys.joint_rot[l])
+        j = quat_mul(a_p * np.array([1.0, -1, -1, -1]), a_c)
+        w, x, y, z = j
+        r00, r01, r02 = 1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)
+        r12, r22 = 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)
+        par_sign = sys.joint_parity[l]
+        ang = [np.arctan2(-r12, r22), np.arctan2(r02, np.hypot(r00, r01)), par_sign * np.arctan2(-r01, r00)]
+        lon = np.array([0.0, r22, -r12])
+        lon = lon / (np.linalg.norm(lon) + 1e-30)
+        axes = [np.array([1.0, 0, 0]), lon, par_sign * np.array([r02, r12, r22])]
+        jd = rotate(xang[l] - pang, a_p * np.array([1.0, -1, -1, -1]))
+        for k in range(nd):
+            q[qs + k] = ang[k]
+            qd[ds + k] = float(np.dot(axes[k], jd))
+    return q.astype(np.float32), qd.astype(np.float32)

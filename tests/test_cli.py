@@ -1,0 +1,65 @@
+"""Args / recommended-parameter override logic (mbd_planner.py:18-35,45-69) and the env registry."""
+import dataclasses
+
+import pytest
+
+import mbd_b200
+from mbd_b200.planners.mbd_planner import Args, apply_recommended_params
+
+
+def test_args_fields_match_reference():
+    names = [f.name for f in dataclasses.fields(Args)]
+    assert names == ["seed", "disable_recommended_params", "not_render", "env_name", "Nsample", "Hsample", "Ndiffuse",
+                     "temp_sample", "beta0", "betaT", "enable_demo"]
+    a = Args()
+    assert (a.seed, a.env_name, a.Nsample, a.Hsample, a.Ndiffuse, a.temp_sample, a.beta0, a.betaT, a.enable_demo) == \
+        (0, "ant", 2048, 50, 100, 0.1, 1e-4, 1e-2, False)
+
+
+def test_recommended_overrides(capsys):
+    a = apply_recommended_params(Args(env_name="humanoidrun", Nsample=16, Ndiffuse=5, temp_sample=0.7))
+    assert (a.Nsample, a.Ndiffuse, a.temp_sample, a.Hsample) == (8192, 300, 0.1, 50)
+    assert "override temp_sample to 0.1" in capsys.readouterr().out
+    a = apply_recommended_params(Args(env_name="pushT"))
+    assert (a.Ndiffuse, a.Hsample, a.temp_sample) == (200, 40, 0.2)
+    a = apply_recommended_params(Args(env_name="halfcheetah"))
+    assert a.temp_sample == 0.4
+    a = apply_recommended_params(Args(env_name="car2d", temp_sample=0.3, Nsample=64))
+    assert (a.temp_sample, a.Nsample, a.Ndiffuse) == (0.3, 64, 100)  # car2d has no recommendation
+    a = apply_recommended_params(Args(env_name="humanoidrun", Nsample=16, disable_recommended_params=True))
+    assert a.Nsample == 16 and a.Ndiffuse == 100
+
+
+def test_tyro_cli_parses_reference_flags():
+    import tyro
+    a = tyro.cli(Args, args=["--env_name", "car2d", "--Nsample", "64", "--Hsample", "40", "--enable_demo", "--not_render"])
+    assert a.env_name == "car2d" and a.Nsample == 64 and a.Hsample == 40 and a.enable_demo and a.not_render
+
+
+def test_env_registry():
+    assert mbd_b200.envs.get_env("car2d").action_size == 2
+    e = mbd_b200.envs.get_env("humanoidrun")
+    assert (e.action_size, e.observation_size, round(e.dt, 6)) == (17, 47, 0.042)
+    t = mbd_b200.envs.get_env("humanoidtrack")
+    assert (t.action_size, round(t.dt, 6), t.xref.shape, t.rew_xref) == (17, 0.03, (5, 50, 3), 1.0)
+    assert t.track_body_idx.tolist() == [0, 5, 3, 6, 4] and t.ref_body_idx.tolist() == [11, 12, 13, 14, 15]
+    with pytest.raises(ValueError, match="Unknown environment"):
+        mbd_b200.envs.get_env("nope")
+    with pytest.raises(NotImplementedError):
+        mbd_b200.envs.get_env("ant")
+
+
+def test_reset_is_the_reference_chain():
+    """humanoidrun.py:19-32: split(rng,3) -> uniform(+-0.01) on q (24) and qd (23)."""
+    import numpy as np
+    from mbd_b200 import prng
+    e = mbd_b200.envs.get_env("humanoidrun")
+    rng, rng_reset = prng.split(prng.PRNGKey(0))
+    st = e.reset(rng_reset)
+    _, r1, r2 = prng.split(rng_reset, 3)
+    q = e.sys.init_q.astype(np.float32) + prng.uniform(r1, (24,), -0.01, 0.01)
+    assert np.allclose(st.pipeline_state.q[7:], q[7:], atol=1e-6)       # hinge angles survive FK -> IK
+    assert np.allclose(st.pipeline_state.q[:3], q[:3], atol=1e-6)
+    assert st.obs.shape == (47,) and st.reward == 0 and st.done == 0
+    st2 = mbd_b200.envs.get_env("humanoidtrack").reset(None)
+    assert np.allclose(st2.pipeline_state.q[7:24], 0, atol=1e-7) and np.allclose(st2.pipeline_state.qd, 0)

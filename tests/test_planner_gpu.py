@@ -1,0 +1,172 @@
+"""reverse_once / run_diffusion on the GPU against the numpy planner oracle (rtol 1e-4, the
+tolerance north_star states for fp32), shard-count invariance (bit-exact) and the env surface."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mbd_b200
+from mbd_b200 import ops, prng
+from mbd_b200.planners import engine as eng
+from mbd_b200.planners.mbd_planner import Args, run_diffusion
+from mbd_b200.planners.sharding import tree_sum_rows
+from oracle import planner as opl
+from tests.conftest import assert_bit_exact
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-4  # north_star: "within 1e-4 relative fp32"
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def _close(a, b, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = max(np.abs(b).max(), 1e-6)
+    err = np.abs(a - b).max() / scale
+    assert err <= RTOL, f"{what}: max rel-to-scale error {err:.3e} > {RTOL}"
+
+
+@pytest.mark.parametrize("demo", [False, True])
+def test_reverse_once_car2d_vs_oracle(orc, demo):
+    car = mbd_b200.envs.get_env("car2d")
+    Nn, H, temp, i = 512, 50, 0.1, 60
+    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 100)
+    key = np.uint32([9, 8])
+    Ybar_i = (np.random.default_rng(0).normal(size=100) * 0.3).astype(np.float32)
+    oenv = opl.OracleEnv("car2d", 2, params=car.params, x0=car.x0)
+    ref = opl.reverse_once(oenv, key, Nn, H, float(sigmas[i]), Ybar_i, temp, alphas, alphas_bar, i,
+                           xref=car.xref if demo else None, rew_xref=car.rew_xref)
+    e = eng.DiffusionEngine(car, Nn, H, temp, demo, car.reset(None))
+    out, rew = e.reverse_once(key, float(sigmas[i]), torch.as_tensor(Ybar_i, device=DEV), eng.update_coef(alphas, alphas_bar, i))
+    assert_bit_exact(N(e.Y0s), ref["Y0s"]); assert_bit_exact(N(e.rews_local), ref["rews"])
+    if demo:
+        assert_bit_exact(N(e.logpd_local), ref["logpd"])
+    _close(N(e.weights), ref["weights"], "softmax weights")
+    _close(N(out), ref["Ybar_im1"], "Ybar_im1")
+    _close(rew.item(), ref["rew_mean"], "rews.mean()")
+    assert abs(N(e.weights).sum() - 1) < 1e-5
+
+
+def test_reverse_once_humanoidrun_vs_oracle(orc, humanoidrun_setup):
+    env, blob, st = humanoidrun_setup
+    Nn, H, temp, i = 256, 50, 0.1, 299
+    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 300)
+    key = prng.split(prng.split(prng.split(prng.PRNGKey(0))[0])[0])[1]
+    Ybar_i = np.zeros(850, np.float32)
+    oenv = opl.OracleEnv("xpbd", 17, blob=blob, state=st)
+    ref = opl.reverse_once(oenv, key, Nn, H, float(sigmas[i]), Ybar_i, temp, alphas, alphas_bar, i)
+    e = eng.DiffusionEngine(env, Nn, H, temp, False, st)
+    out, rew = e.reverse_once(key, float(sigmas[i]), torch.zeros(850, device=DEV), eng.update_coef(alphas, alphas_bar, i))
+    assert_bit_exact(N(e.rews_local), ref["rews"], "per-sample returns")
+    _close(N(out), ref["Ybar_im1"], "Ybar_im1"); _close(rew.item(), ref["rew_mean"], "rews.mean()")
+    # index work is bit-exact: the best sample is the same one
+    assert int(N(e.weights).argmax()) == int(ref["weights"].argmax())
+
+
+def test_reverse_once_humanoidtrack_demo_vs_oracle(orc):
+    env = mbd_b200.envs.get_env("humanoidtrack")
+    st = env.reset(None).pipeline_state.raw
+    Nn, H, temp, i = 128, 50, 0.1, 80
+    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 100)
+    key = np.uint32([77, 1])
+    oenv = opl.OracleEnv("xpbd", 17, blob=env.blob, state=st)
+    ref = opl.reverse_once(oenv, key, Nn, H, float(sigmas[i]), np.zeros(850, np.float32), temp, alphas, alphas_bar, i,
+                           xref=env.xref, rew_xref=env.rew_xref)
+    e = eng.DiffusionEngine(env, Nn, H, temp, True, st)
+    out, rew = e.reverse_once(key, float(sigmas[i]), torch.zeros(850, device=DEV), eng.update_coef(alphas, alphas_bar, i))
+    assert_bit_exact(N(e.rews_local), ref["rews"]); assert_bit_exact(N(e.logpd_local), ref["logpd"])
+    _close(N(e.weights), ref["weights"], "weights (demo blend)"); _close(N(out), ref["Ybar_im1"], "Ybar_im1")
+
+
+def test_std_guard_uniform_weights():
+    """rews.std() < 1e-4 -> 1 (mbd_planner.py:112): constant rewards give uniform weights."""
+    n = 256
+    rews = torch.full((n,), 0.25, device=DEV)
+    w = torch.empty(n, device=DEV); sc = torch.zeros(4, device=DEV); scratch = torch.empty(n, device=DEV)
+    ops.softmax_weights(rews, None, 0, n, 0.1, 0.0, w, sc, scratch)
+    assert np.allclose(N(w), 1 / n, rtol=1e-6) and N(sc)[1] == 1.0 and np.isclose(N(sc)[0], 0.25)
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_shard_count_invariance_bit_exact(humanoidrun_setup, P):
+    """Emulates P ranks on one GPU with the same kernels/arguments each rank would use:
+    the combined result equals the single-rank result bit for bit."""
+    env, blob, st = humanoidrun_setup
+    Nn, H, temp = 1024, 50, 0.1
+    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 100)
+    coef = eng.update_coef(alphas, alphas_bar, 70)
+    key = np.uint32([4, 4]); Ybar_i = torch.zeros(850, device=DEV)
+    e1 = eng.DiffusionEngine(env, Nn, H, temp, False, st)
+    full, _ = e1.reverse_once(key, float(sigmas[70]), Ybar_i, coef)
+    full = N(full).copy()
+    m = env.device_model(torch.device(DEV)); sti = torch.as_tensor(st, device=DEV)
+    nl = Nn // P
+    rews_all = torch.empty(Nn, device=DEV); Ys = []
+    for r in range(P):
+        Y = torch.empty((nl, 850), device=DEV)
+        ops.sample_rollout(m, sti, key, Nn, r * nl, nl, H, float(sigmas[70]), Ybar_i, Y, rews_all[r * nl:(r + 1) * nl])
+        Ys.append(Y)
+    assert_bit_exact(N(rews_all), N(e1.rews_all))
+    partials = torch.empty((P, 850), device=DEV)
+    for r in range(P):
+        w = torch.empty(nl, device=DEV); sc = torch.zeros(4, device=DEV); scratch = torch.empty(Nn, device=DEV)
+        ops.softmax_weights(rews_all, None, r * nl, nl, temp, 0.0, w, sc, scratch)
+        runs = torch.empty(((nl + 63) // 64) * 850, device=DEV)
+        ops.weighted_sum(w, Ys[r], 850, runs, partials[r])
+    out = torch.empty(850, device=DEV)
+    ops.update(partials, P, 850, Ybar_i, coef, out)
+    assert_bit_exact(N(out), full, f"P={P} vs P=1")
+    # the host-side mirror of the rank combine agrees too
+    Yi = Ybar_i * float(coef[0])
+    host = (float(coef[3]) * (Yi + float(coef[2]) * (float(coef[1]) * (-Yi + float(coef[0]) * tree_sum_rows(partials))))) / float(coef[4])
+    assert np.allclose(N(host), full, rtol=1e-6, atol=1e-7)
+
+
+def test_run_diffusion_car2d_matches_oracle_solve(orc, capsys):
+    """BASELINE config 1 (car2d, Nsample=64, Hsample=40, full solve) + a demo solve, end to end
+    through the reference-facing API."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "car2d_oracle.npz"))
+    rf, Yi = run_diffusion(Args(env_name="car2d", Nsample=64, Hsample=40, not_render=True), return_trajectory=True)
+    out = capsys.readouterr().out
+    assert "override temp_sample to 0.1" in out and "init sigma = 6.30e-01" in out
+    assert Yi.shape == (99, 40, 2)
+    _close(N(Yi[-1]).reshape(-1), g["Yi_last"], "final iterate"); _close(rf, float(g["rew_final"]), "rew_final")
+    rfd, Yid = run_diffusion(Args(env_name="car2d", Nsample=512, Hsample=50, enable_demo=True, not_render=True), return_trajectory=True)
+    # 99 chained softmax steps amplify rounding differences of the statistics: compare loosely
+    assert abs(rfd - float(g["rew_final_demo"])) < 0.05
+    assert np.abs(N(Yid[-1]).reshape(-1) - g["Yi_last_demo"]).max() < 0.05
+
+
+def test_run_diffusion_humanoidrun_short(humanoidrun_setup, tmp_path, monkeypatch):
+    """a short humanoidrun solve through Args/run_diffusion: artefact shape + improving reward"""
+    a = Args(env_name="humanoidrun", Nsample=512, Ndiffuse=12, disable_recommended_params=True, not_render=True)
+    rf, Yi = run_diffusion(a, return_trajectory=True)
+    assert Yi.shape == (11, 50, 17) and np.isfinite(N(Yi)).all() and np.isfinite(rf)
+    assert float(N(Yi).max()) <= 1.0 and float(N(Yi).min()) >= -1.0
+
+
+def test_env_surface_step_equals_rollout(orc, humanoidrun_setup):
+    """env.reset/step (reference surface) steps the same kernel: H single steps == one rollout."""
+    env, blob, st = humanoidrun_setup
+    rng, rng_reset = prng.split(prng.PRNGKey(0))
+    state = env.reset(rng_reset)
+    us = np.clip(np.random.default_rng(3).normal(size=(6, 17)), -1, 1).astype(np.float32)
+    rews = []
+    for t in range(6):
+        state = env.step(state, us[t]); rews.append(state.reward)
+    ref = orc.xpbd_rollout(blob, st, us[None], want_rewss=True, want_final=True)
+    assert_bit_exact(np.float32(rews), ref["rewss"][0]); assert_bit_exact(state.pipeline_state.raw, ref["final"][0])
+    assert state.obs.shape == (47,)
+    assert np.isclose(state.reward, env._get_reward(state.pipeline_state), atol=1e-5)
+    r2 = mbd_b200.utils.eval_us(env.step, env.reset(rng_reset), us)
+    assert_bit_exact(r2, ref["rewss"][0])
+    car = mbd_b200.envs.get_env("car2d")
+    s = car.reset(None)
+    s = car.step(s, np.float32([0.3, 1.0]))
+    assert s.pipeline_state.shape == (3,) and s.pipeline_state[0] < -0.5
+    rr, xs = mbd_b200.utils.rollout_us(car.step, car.reset(None), np.float32([[0.3, 1.0]] * 3))
+    assert len(xs) == 3 and np.allclose(xs[0], s.pipeline_state)
