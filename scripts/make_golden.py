@@ -45,6 +45,10 @@ car = mbd_b200.envs.get_env("car2d")
 oenv = opl.OracleEnv("car2d", 2, params=car.params, x0=car.x0)
 rf, Yi, rews = opl.run_diffusion(oenv, 0, 64, 40, 100, 0.1)
 rfd, Yid, rewsd = opl.run_diffusion(oenv, 0, 512, 50, 100, 0.1, xref=car.xref, rew_xref=car.rew_xref)
+# short demo chain (8 steps): long chains amplify rounding differences of the statistics through the
+# collision freeze / reward clip discontinuities, so step-level parity is pinned on a short one
+rfs, Yis, rewss_ = opl.run_diffusion(oenv, 0, 512, 50, 9, 0.1, xref=car.xref, rew_xref=car.rew_xref)
 np.savez_compressed(os.path.join(G, "car2d_oracle.npz"), rew_final=np.float32(rf), Yi_last=Yi[-1], rews=rews,
-                    rew_final_demo=np.float32(rfd), Yi_last_demo=Yid[-1], rews_demo=rewsd)
+                    rew_final_demo=np.float32(rfd), Yi_last_demo=Yid[-1], rews_demo=rewsd,
+                    Yi_short_demo=Yis, rews_short_demo=rewss_)
 print("car2d", rf, rfd)
