@@ -56,7 +56,7 @@ def lib():
     return L
 
 
-EXPORTS = ["mbd_layout_info", "mbd_last_error", "mbd_device_count", "mbd_model_create", "mbd_model_destroy", "mbd_sample",
+EXPORTS = ["mbd_set_kernel_variant", "mbd_layout_info", "mbd_last_error", "mbd_device_count", "mbd_model_create", "mbd_model_destroy", "mbd_sample",
            "mbd_rollout", "mbd_sample_rollout", "mbd_car2d_rollout", "mbd_softmax_weights", "mbd_weighted_sum", "mbd_update"]
 
 

@@ -13,10 +13,13 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "mbd_b200.h"
 #include "mbd_fp32.h"
 #include "mbd_model.h"
 #include "xpbd_device.cuh"
+#include "xpbd_wpl.cuh"
 
 namespace mbd {
 
@@ -224,6 +227,144 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
   }
 }
 
+// ---- v2 rollout kernel: warp per link, lane per sample (xpbd_wpl.cuh) -------------------------------------
+template <bool FUSED, int NWARPS, int MINB, int SYNC>
+__global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a) {
+  __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t edge_bars[2 * MBD_MAXL];
+  extern __shared__ __align__(16) float dyn[];
+  stage_model_tma(sblob, &mbar, a.blob);
+  ModelSmem M;
+  M.f = sblob;
+
+  const int tid = threadIdx.x, lane = tid & 31, l = tid >> 5;  // warp = link
+  const int L = M.hi(MBD_H_NLINK), nu = M.hi(MBD_H_NU);
+  const int HNu = a.H * nu;
+  const int nsub = a.nsub_override > 0 ? a.nsub_override : M.hi(MBD_H_NFRAMES);
+  const int reward_kind = M.hi(MBD_H_REWARD);
+  const int ntrack = M.hi(MBD_H_NTRACK);
+  const int nthreads = 32 * L;
+
+  if (FUSED) {
+    const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+    const int first = blockIdx.x * kWplLanes;
+    const int cnt = min(kWplLanes, a.n - first) * HNu;
+    for (int e = tid; e < cnt; e += nthreads) {
+      int ns = first + e / HNu, j = e % HNu;
+      uint32_t idx = (uint32_t)(a.n_begin + ns) * (uint32_t)HNu + (uint32_t)j;
+      a.Y0s[(size_t)ns * HNu + j] = sample_elem(a.k0, a.k1, idx, total, a.sigma, a.Ybar[j]);
+    }
+    __syncthreads();
+  }
+
+  WplSmem S;
+  S.X = dyn;
+  S.E = dyn + L * kXF * kWplLanes;
+  S.lane = lane;
+  WarpCfg c;
+  load_warp_cfg(M, l, c);
+
+  const int n_local = blockIdx.x * kWplLanes + lane;
+  const bool active = n_local < a.n;
+  const int n_rd = active ? n_local : a.n - 1;
+
+  LinkState s;
+  {
+    const float* st = a.state_init + l * MBD_STATE_STRIDE;
+    s.p = V3(st[0], st[1], st[2]);
+    s.q = Q4(st[3], st[4], st[5], st[6]);
+    s.w = V3(st[7], st[8], st[9]);
+    s.v = V3(st[10], st[11], st[12]);
+  }
+  S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
+  typename std::conditional<SYNC == 1, SyncP2P, typename std::conditional<SYNC == 2, SyncNamed, SyncCta>::type>::type Y;
+  if constexpr (SYNC == 2) Y.setup(M, l, L);
+  if constexpr (SYNC == 1) {
+    Y.pose = edge_bars; Y.terms = edge_bars + MBD_MAXL; Y.ph_pose = 0u; Y.ph_terms = 0u;
+    if (tid < 2 * MBD_MAXL) asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_u32(&edge_bars[tid])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  int aid[MBD_MAXDOF];
+#pragma unroll
+  for (int k = 0; k < MBD_MAXDOF; ++k) aid[k] = k < c.ndof ? M.li(MBD_F_DOF0 + k * MBD_DOF_STRIDE + MBD_D_ACT, l) : -1;
+  int my_track = -1;
+  for (int k = 0; k < ntrack; ++k)
+    if (M.hi(MBD_H_TRACK0 + k) == l) my_track = k;
+  __syncthreads();
+  if constexpr (SYNC != 0) Y.arrive_pose(l);  // the initial pose is published
+
+  float rsum = 0.0f, tacc = 0.0f;
+  const float* urow = a.Y0s + (size_t)n_rd * HNu;
+  for (int t = 0; t < a.H; ++t) {
+    float tau[MBD_MAXDOF];
+#pragma unroll
+    for (int k = 0; k < MBD_MAXDOF; ++k) {
+      const int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+      float u = aid[k] >= 0 ? urow[t * nu + aid[k]] : 0.0f;
+      tau[k] = aid[k] >= 0 ? M.lf(base + MBD_D_GEAR, l) * clampf(u, M.lf(base + MBD_D_CLO, l), M.lf(base + MBD_D_CHI, l)) : 0.0f;
+    }
+    float r_pre = 0.0f;
+    if (reward_kind == MBD_REWARD_HUMANOIDTRACK && l == 0) {
+      v3 x0 = link_origin_w(M, 0, s);
+      v3 v0 = link_origin_vel_w(M, 0, s);
+      r_pre = 1.0f + ((-fabsf(v0.x - 1.6f) - fabsf(x0.z - 1.3f)) - fabsf(x0.y) * 0.1f);
+    }
+    for (int f = 0; f < nsub; ++f) positional_step_wpl(M, c, S, Y, s, tau);
+    if (l == 0) {
+      float r;
+      if (reward_kind == MBD_REWARD_HUMANOIDTRACK) {
+        r = r_pre;
+      } else {
+        v3 x0 = link_origin_w(M, 0, s);
+        if (reward_kind == MBD_REWARD_HUMANOIDRUN) {
+          float dz = clampf(fabsf(x0.z - 1.3f), -1.0f, 1.0f);
+          r = (x0.x - dz) - fabsf(x0.y) * 0.1f;
+        } else {
+          r = x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;
+        }
+      }
+      rsum += r;
+      if (a.rewss && active) a.rewss[(size_t)n_local * a.H + t] = r;
+    }
+    if (my_track >= 0) {
+      v3 x = link_origin_w(M, l, s);
+      if (a.track_pos && active) {
+        float* o = a.track_pos + (((size_t)n_local * a.H + t) * ntrack + my_track) * 3;
+        o[0] = x.x; o[1] = x.y; o[2] = x.z;
+      }
+      if (a.xref) {
+        int tt = t < a.href ? t : a.href - 1;
+        const float* xr = a.xref + ((size_t)my_track * a.href + tt) * 3;
+        v3 d = V3(x.x - xr[0], x.y - xr[1], x.z - xr[2]);
+        float nr = sqrtf(vdot(d, d));
+        float cl = nr < 0.5f ? nr : 0.5f;
+        float q = cl / 0.5f;
+        tacc = fmaf(q, q, tacc);
+      }
+    }
+  }
+  if (l == 0 && active) a.rews[n_local] = rsum / (float)a.H;
+  if (a.logpd && a.xref) {
+    // per-body accumulators -> shared (reuse E), summed in track order by warp 0
+    __syncthreads();  // every warp is done with E
+    if (my_track >= 0) S.E[my_track * kWplLanes + lane] = tacc;
+    __syncthreads();
+    if (l == 0 && active) {
+      float tot = 0.0f;
+      for (int k = 0; k < ntrack; ++k) tot += S.E[k * kWplLanes + lane];
+      a.logpd[n_local] = 0.0f - tot / (float)(ntrack * a.H);
+    }
+  }
+  if (a.final_state && active) {
+    float* o = a.final_state + ((size_t)n_local * L + l) * MBD_STATE_STRIDE;
+    o[0] = s.p.x; o[1] = s.p.y; o[2] = s.p.z;
+    o[3] = s.q.w; o[4] = s.q.x; o[5] = s.q.y; o[6] = s.q.z;
+    o[7] = s.w.x; o[8] = s.w.y; o[9] = s.w.z;
+    o[10] = s.v.x; o[11] = s.v.y; o[12] = s.v.z;
+  }
+}
+
 // ---- car2d (/root/reference/mbd/envs/car2d.py) ---------------------------------------------------------
 constexpr int kCarObs = 11;
 __device__ __forceinline__ void car_dynamics(const float* x, const float* u, float* o) {
@@ -416,6 +557,7 @@ struct mbd_model {
   int L, nu, n_frames, ntrack;
 };
 
+static int g_kernel_variant = 0;  // 0 = auto, 1 = v1 (lane per link), 2..4 = v2 (warp per link; CTA / named / mbarrier sync)
 static thread_local char g_err[256] = "";
 static int set_err(const char* where, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
@@ -435,6 +577,12 @@ int mbd_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   return n;
+}
+
+int mbd_set_kernel_variant(int v) {
+  if (v < 0 || v > 4) return MBD_EINVAL;
+  g_kernel_variant = v;
+  return MBD_OK;
 }
 
 int mbd_layout_info(int32_t* out, int n) {
@@ -485,12 +633,40 @@ int mbd_sample(const uint32_t key[2], int n_total, int n_begin, int n_local, int
   return MBD_OK;
 }
 
-static int launch_rollout(bool fused, const mbd::RolloutArgs& a, cudaStream_t st) {
-  int grid = (a.n + mbd::kSPB - 1) / mbd::kSPB;
-  if (fused)
-    mbd::k_rollout<true><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
-  else
-    mbd::k_rollout<false><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+static int launch_rollout(bool fused, const mbd::RolloutArgs& a, int L, cudaStream_t st) {
+  int variant = g_kernel_variant;
+  if (variant == 0) variant = (a.n >= 4096 || L != 11) ? 2 : 1;  // small shards: the lane-per-link kernel has more warps in flight
+  if (variant >= 2) {
+    int grid = (a.n + mbd::kWplLanes - 1) / mbd::kWplLanes;
+    size_t dyn = (size_t)L * (mbd::kXF + mbd::kEF) * mbd::kWplLanes * sizeof(float);
+    if (L == 11 && variant == 3) {  // named edge barriers (shorter chain, best for 1 CTA/SM)
+      if (fused)
+        mbd::k_rollout_wpl<true, 11, 2, 2><<<grid, 32 * L, dyn, st>>>(a);
+      else
+        mbd::k_rollout_wpl<false, 11, 2, 2><<<grid, 32 * L, dyn, st>>>(a);
+    } else if (L == 11 && variant == 2) {  // the humanoids: 352 threads, 2 CTAs/SM (<= 88 registers), CTA-wide barriers
+      if (fused)
+        mbd::k_rollout_wpl<true, 11, 2, 0><<<grid, 32 * L, dyn, st>>>(a);
+      else
+        mbd::k_rollout_wpl<false, 11, 2, 0><<<grid, 32 * L, dyn, st>>>(a);
+    } else if (L == 11 && variant == 4) {  // mbarrier point-to-point (polling)
+      if (fused)
+        mbd::k_rollout_wpl<true, 11, 2, 1><<<grid, 32 * L, dyn, st>>>(a);
+      else
+        mbd::k_rollout_wpl<false, 11, 2, 1><<<grid, 32 * L, dyn, st>>>(a);
+    } else {
+      if (fused)
+        mbd::k_rollout_wpl<true, MBD_MAXL, 1, 0><<<grid, 32 * L, dyn, st>>>(a);
+      else
+        mbd::k_rollout_wpl<false, MBD_MAXL, 1, 0><<<grid, 32 * L, dyn, st>>>(a);
+    }
+  } else {
+    int grid = (a.n + mbd::kSPB - 1) / mbd::kSPB;
+    if (fused)
+      mbd::k_rollout<true><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+    else
+      mbd::k_rollout<false><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+  }
   CK(cudaGetLastError());
   return MBD_OK;
 }
@@ -505,7 +681,7 @@ int mbd_rollout(const mbd_model* m, const float* state_init_dev, const float* Y0
   a.blob = m->blob_dev; a.state_init = state_init_dev; a.Y0s = const_cast<float*>(Y0s_dev); a.n = n; a.H = H;
   a.rewss = rewss_dev; a.rews = rews_dev; a.xref = xref_dev; a.href = href; a.logpd = logpd_dev;
   a.final_state = final_state_dev; a.track_pos = track_pos_dev; a.nsub_override = nsub_override;
-  return launch_rollout(false, a, (cudaStream_t)s);
+  return launch_rollout(false, a, m->L, (cudaStream_t)s);
 }
 
 int mbd_sample_rollout(const mbd_model* m, const float* state_init_dev, const uint32_t key[2], int n_total, int n_begin, int n_local,
@@ -520,7 +696,7 @@ int mbd_sample_rollout(const mbd_model* m, const float* state_init_dev, const ui
   a.blob = m->blob_dev; a.state_init = state_init_dev; a.Y0s = Y0s_dev; a.n = n_local; a.H = H;
   a.rews = rews_dev; a.xref = xref_dev; a.href = href; a.logpd = logpd_dev;
   a.k0 = key[0]; a.k1 = key[1]; a.n_total = n_total; a.n_begin = n_begin; a.sigma = sigma; a.Ybar = Ybar_dev;
-  return launch_rollout(true, a, (cudaStream_t)s);
+  return launch_rollout(true, a, m->L, (cudaStream_t)s);
 }
 
 int mbd_car2d_rollout(const float* params_dev, const float* x0_dev, const uint32_t* key, int n_total, int n_begin, int n_local, int H,

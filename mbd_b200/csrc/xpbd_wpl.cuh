@@ -1,0 +1,417 @@
+// xpbd_wpl.cuh — "warp per link, lane per sample" rollout kernel (v2).
+//
+// v1 (xpbd_device.cuh) maps one LINK per LANE: ncu showed 16.9 of 32 lanes active on average and
+// 31 % of all issue slots spent in the contact code with <= 4 active lanes.  v2 transposes the
+// mapping: a CTA owns 32 samples, warp w owns link w of all 32, lane = sample.  Every branch on
+// the link's properties (jointed? ndof? contacts?) is warp-uniform, so no lane is ever masked,
+// and joint-type specialisation (1-dof links skip the two unused Euler angles) is free.
+// The link state (x_i, xd_i, x_i_prev, xd_i_before) stays in registers for the whole rollout;
+// what other links need (parent pose, child reaction terms) is exchanged through shared memory,
+// [link][field][lane] (conflict-free), with four CTA barriers per physics step:
+//     A  joint torques        -> E[l] = T_l            | bar
+//     B  gather children T, integrate, publish p,q     | bar
+//     C  XPBD joint deltas     -> E[l] = parent deltas  | bar
+//     D  gather children deltas, apply, contacts, project_xd, contact velocities, publish q,w | bar
+// The arithmetic (association order, fmaf placement, child gather order) is IDENTICAL to v1 and
+// to oracle/mbd_oracle.c: results are bit-exact across all three.
+#pragma once
+
+#include "xpbd_device.cuh"
+
+namespace mbd {
+
+constexpr int kWplLanes = 32;
+constexpr int kXF = 10;  // published pose fields per link: p(3) q(4) w(3)
+constexpr int kEF = 7;   // exchange fields per link: T(3)  |  dpp(3) dqp(4)
+
+struct WplSmem {
+  float* X;  // [L][kXF][32]
+  float* E;  // [L][kEF][32]
+  int lane;
+  __device__ __forceinline__ float& x(int link, int f) const { return X[(link * kXF + f) * kWplLanes + lane]; }
+  __device__ __forceinline__ float& e(int link, int f) const { return E[(link * kEF + f) * kWplLanes + lane]; }
+  __device__ __forceinline__ v3 xp(int link) const { return V3(x(link, 0), x(link, 1), x(link, 2)); }
+  __device__ __forceinline__ q4 xq(int link) const { return Q4(x(link, 3), x(link, 4), x(link, 5), x(link, 6)); }
+  __device__ __forceinline__ v3 xw(int link) const { return V3(x(link, 7), x(link, 8), x(link, 9)); }
+  __device__ __forceinline__ void put_p(int link, v3 p) const { x(link, 0) = p.x; x(link, 1) = p.y; x(link, 2) = p.z; }
+  __device__ __forceinline__ void put_q(int link, q4 q) const { x(link, 3) = q.w; x(link, 4) = q.x; x(link, 5) = q.y; x(link, 6) = q.z; }
+  __device__ __forceinline__ void put_w(int link, v3 w) const { x(link, 7) = w.x; x(link, 8) = w.y; x(link, 9) = w.z; }
+  __device__ __forceinline__ v3 e3(int link, int f) const { return V3(e(link, f), e(link, f + 1), e(link, f + 2)); }
+  __device__ __forceinline__ q4 e4(int link, int f) const { return Q4(e(link, f), e(link, f + 1), e(link, f + 2), e(link, f + 3)); }
+  __device__ __forceinline__ void put_e3(int link, int f, v3 a) const { e(link, f) = a.x; e(link, f + 1) = a.y; e(link, f + 2) = a.z; }
+  __device__ __forceinline__ void put_e4(int link, int f, q4 a) const { e(link, f) = a.w; e(link, f + 1) = a.x; e(link, f + 2) = a.y; e(link, f + 3) = a.z; }
+};
+
+// warp-uniform link configuration
+// Only the integer topology stays in registers; the float constants are warp-uniform and are read
+// from the shared-memory model table where they are used (broadcast LDS) — caching them cost ~40
+// registers per thread and forced spills under the 2-CTAs/SM register cap.
+struct WarpCfg {
+  int l, ndof, parent, ncon;
+  int child[MBD_MAXCHILD];
+};
+
+__device__ __forceinline__ void load_warp_cfg(const ModelSmem& M, int l, WarpCfg& c) {
+  c.l = l;
+  c.ndof = M.li(MBD_F_NDOF, l);
+  c.parent = M.li(MBD_F_PARENT, l);
+  c.ncon = M.li(MBD_F_NCON, l);
+#pragma unroll
+  for (int k = 0; k < MBD_MAXCHILD; ++k) c.child[k] = M.li(MBD_F_CHILD0 + k, l);
+}
+
+// axis_angle_ang specialised for 1-dof links: only psi and the extra matrix entries are used
+// (oracle computes the rest and discards it — same bits for what is used).
+__device__ __forceinline__ void axis_angle_1dof(q4 j, float& psi, float& r10, float& r20) {
+  float w = j.w, x = j.x, y = j.y, z = j.z;
+  float r12 = 2.0f * fmaf(y, z, -(w * x));
+  float r22 = 1.0f - 2.0f * fmaf(y, y, x * x);
+  r10 = 2.0f * fmaf(x, y, w * z);
+  r20 = 2.0f * fmaf(x, z, -(w * y));
+  psi = mbd_atan2f(-r12, r22);
+}
+
+// ---- synchronisation policies --------------------------------------------------------------------
+// SyncCta: four CTA-wide barriers per physics step (simple, any tree).
+// SyncP2P: point-to-point mbarriers along the tree edges — link l owns two mbarriers (count 32):
+//   pose[l]  : l arrives after publishing its pose (phases B, D); its CHILDREN wait on it (A, C)
+//   terms[l] : l arrives after writing its parent-directed terms (A, C); its PARENT waits (B, D)
+// so unrelated limbs never wait for each other and leaves (the shins with their contact work)
+// never hold up anybody but their own parent.  No lapping is possible: a producer's next
+// arrival on either barrier transitively requires its consumers to have passed the wait.
+struct SyncCta {
+  __device__ __forceinline__ void wait_pose(int) {}
+  __device__ __forceinline__ void arrive_terms(int) {}
+  __device__ __forceinline__ void wait_terms(const int*) {}
+  __device__ __forceinline__ void arrive_pose(int) {}
+  __device__ __forceinline__ void phase_end() { __syncthreads(); }
+};
+
+struct SyncP2P {
+  uint64_t* pose;   // [L]
+  uint64_t* terms;  // [L]
+  uint32_t ph_pose, ph_terms;
+  static __device__ __forceinline__ uint32_t a32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+  static __device__ __forceinline__ void arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a32(b)) : "memory");
+  }
+  static __device__ __forceinline__ void wait(uint64_t* b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(a32(b)), "r"(parity)
+          : "memory");
+    }
+  }
+  __device__ __forceinline__ void wait_pose(int parent) {
+    if (parent >= 0) wait(&pose[parent], ph_pose);
+    ph_pose ^= 1u;
+  }
+  __device__ __forceinline__ void arrive_terms(int l) { arrive(&terms[l]); }
+  __device__ __forceinline__ void wait_terms(const int* child) {
+#pragma unroll
+    for (int k = 0; k < MBD_MAXCHILD; ++k)
+      if (child[k] >= 0) wait(&terms[child[k]], ph_terms);
+    ph_terms ^= 1u;
+  }
+  __device__ __forceinline__ void arrive_pose(int l) { arrive(&pose[l]); }
+  __device__ __forceinline__ void phase_end() {}
+};
+
+// SyncNamed: the same edge protocol on hardware named barriers (bar.arrive / bar.sync, ids 1..15):
+// waiting warps sleep in the barrier unit instead of polling an mbarrier, so they do not steal
+// issue slots from the working warps.  Each node WITH children owns two ids:
+//   pose id : the node bar.arrive's, each child bar.sync's      (count = 32 * (1 + nchildren))
+//   terms id: each child bar.arrive's, the node bar.sync's      (same count)
+// Needs 2 * (#nodes with children) <= 15; otherwise the caller falls back to SyncCta.
+struct SyncNamed {
+  int my_pose_id, my_terms_id, my_count;       // valid when this link has children (else 0)
+  int par_pose_id, par_terms_id, par_count;    // ids owned by the parent (0 when parent is the world / none)
+  static __device__ __forceinline__ void bar_arrive(int id, int count) {
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+  }
+  static __device__ __forceinline__ void bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void wait_pose(int parent) {
+    if (parent >= 0) bar_sync(par_pose_id, par_count);
+  }
+  __device__ __forceinline__ void arrive_terms(int) {
+    if (par_terms_id) bar_arrive(par_terms_id, par_count);
+  }
+  __device__ __forceinline__ void wait_terms(const int*) {
+    if (my_terms_id) bar_sync(my_terms_id, my_count);
+  }
+  __device__ __forceinline__ void arrive_pose(int) {
+    if (my_pose_id) bar_arrive(my_pose_id, my_count);
+  }
+  __device__ __forceinline__ void phase_end() {}
+  // returns false when the tree needs more ids than the hardware has
+  __device__ __forceinline__ bool setup(const ModelSmem& M, int l, int L) {
+    int nparents = 0, my_idx = -1, par_idx = -1, my_nch = 0, par_nch = 0;
+    const int parent = M.li(MBD_F_PARENT, l);
+    const bool jointed = M.li(MBD_F_NDOF, l) > 0;
+    for (int k = 0; k < L; ++k) {
+      int nch = 0;
+      for (int j = 0; j < MBD_MAXCHILD; ++j) nch += M.li(MBD_F_CHILD0 + j, k) >= 0;
+      if (nch > 0) {
+        if (k == l) { my_idx = nparents; my_nch = nch; }
+        if (k == parent) { par_idx = nparents; par_nch = nch; }
+        ++nparents;
+      }
+    }
+    my_pose_id = my_idx >= 0 ? 1 + 2 * my_idx : 0;
+    my_terms_id = my_idx >= 0 ? 2 + 2 * my_idx : 0;
+    my_count = 32 * (1 + my_nch);
+    const bool linked = jointed && par_idx >= 0;
+    par_pose_id = linked ? 1 + 2 * par_idx : 0;
+    par_terms_id = linked ? 2 + 2 * par_idx : 0;
+    par_count = 32 * (1 + par_nch);
+    return 2 * nparents <= 15;
+  }
+};
+
+// One brax.positional.pipeline.step for (link = this warp, sample = this lane).
+// All threads of the CTA must call.
+template <class Sync>
+__device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const WarpCfg& c, const WplSmem& S,
+                                                    Sync& Y, LinkState& s, const float tau[MBD_MAXDOF]) {
+  const bool jointed = c.ndof > 0;
+  const bool has_parent = c.parent >= 0;
+  const v3 p_prev = s.p;
+  const q4 q_prev = s.q;  // x_i_prev
+
+  // ---- A: joints.acceleration_update ----------------------------------------------------------
+  v3 T = V3(0.0f, 0.0f, 0.0f);
+  Y.wait_pose(jointed ? c.parent : -1);
+  if (jointed) {
+    q4 qp = Q4(1.0f, 0.0f, 0.0f, 0.0f);
+    v3 wp = V3(0.0f, 0.0f, 0.0f);
+    if (has_parent) { qp = S.xq(c.parent); wp = S.xw(c.parent); }
+    q4 a_p = qmul(qp, M.l4(MBD_F_PQ, c.l));
+    q4 a_c = qmul(s.q, M.l4(MBD_F_JQ, c.l));
+    q4 j = qmul(qconj(a_p), a_c);
+    v3 jd = vinv_rotate(vsub(s.w, wp), a_p);
+    v3 tq = vscale(jd, -M.lf(MBD_F_ANG_DAMP, c.l));
+    if (c.ndof == 1) {
+      float psi, r10, r20;
+      axis_angle_1dof(j, psi, r10, r20);
+      float vel = vdot(V3(1.0f, 0.0f, 0.0f), jd);
+      float t = fmaf(-M.lf(MBD_F_DOF0 + MBD_D_DAMP, c.l), vel, fmaf(-M.lf(MBD_F_DOF0 + MBD_D_STIFF, c.l), psi, tau[0]));
+      tq = vfma(V3(1.0f, 0.0f, 0.0f), t, tq);
+    } else {
+      JointAngles ja;
+      axis_angle_ang(j, M.lf(MBD_F_PARITY, c.l), ja);
+#pragma unroll
+      for (int k = 0; k < MBD_MAXDOF; ++k) {
+        if (k < c.ndof) {
+          int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+          float vel = vdot(ja.ax[k], jd);
+          float t = fmaf(-M.lf(base + MBD_D_DAMP, c.l), vel, fmaf(-M.lf(base + MBD_D_STIFF, c.l), ja.ang[k], tau[k]));
+          tq = vfma(ja.ax[k], t, tq);
+        }
+      }
+    }
+    T = vrotate(tq, a_p);
+    S.put_e3(c.l, 0, T);
+  }
+  Y.arrive_terms(c.l);
+  Y.phase_end();
+  // ---- B: gather reaction torques, integrator.integrate_xdd, publish pose ---------------------------
+  Y.wait_terms(c.child);
+  {
+    v3 acc = T;
+#pragma unroll
+    for (int k = 0; k < MBD_MAXCHILD; ++k)
+      if (c.child[k] >= 0) acc = vsub(acc, S.e3(c.child[k], 0));
+    s.w = V3(fmaf(acc.x, M.hf(MBD_H_DT), s.w.x * M.hf(MBD_H_ANG_DAMP)), fmaf(acc.y, M.hf(MBD_H_DT), s.w.y * M.hf(MBD_H_ANG_DAMP)), fmaf(acc.z, M.hf(MBD_H_DT), s.w.z * M.hf(MBD_H_ANG_DAMP)));
+    s.v = V3(fmaf(M.hf(MBD_H_GX), M.hf(MBD_H_DT), s.v.x * M.hf(MBD_H_VEL_DAMP)), fmaf(M.hf(MBD_H_GY), M.hf(MBD_H_DT), s.v.y * M.hf(MBD_H_VEL_DAMP)), fmaf(M.hf(MBD_H_GZ), M.hf(MBD_H_DT), s.v.z * M.hf(MBD_H_VEL_DAMP)));
+    s.q = qnormalize(qadd(s.q, vqmul(vscale(s.w, M.hf(MBD_H_HALF_DT)), s.q)));
+    s.p = vfma(s.v, M.hf(MBD_H_DT), s.p);
+    S.put_p(c.l, s.p);
+    S.put_q(c.l, s.q);
+  }
+  Y.arrive_pose(c.l);
+  const v3 w_before = s.w, v_before = s.v;
+  Y.phase_end();
+  // ---- C: joints.position_update ---------------------------------------------------------------------
+  v3 dpc = V3(0.0f, 0.0f, 0.0f);
+  q4 dqc = Q4(0.0f, 0.0f, 0.0f, 0.0f);
+  Y.wait_pose(jointed ? c.parent : -1);
+  if (jointed) {
+    v3 pp = V3(0.0f, 0.0f, 0.0f);
+    q4 qp = Q4(1.0f, 0.0f, 0.0f, 0.0f);
+    if (has_parent) { pp = S.xp(c.parent); qp = S.xq(c.parent); }
+    const float im_c = M.lf(MBD_F_INV_MASS, c.l), im_p = M.lf(MBD_F_PINV_MASS, c.l), ii_p = M.lf(MBD_F_PINV_INERTIA, c.l);
+    v3 rpw = vrotate(M.l3(MBD_F_RP, c.l), qp);
+    v3 rcw = vrotate(M.l3(MBD_F_RC, c.l), s.q);
+    v3 e = vsub(vadd(s.p, rcw), vadd(pp, rpw));
+    float cn;
+    v3 n = vnormalize(e, &cn);
+    v3 crc = vcross(rcw, n), crp = vcross(rpw, n);
+    float w_c = im_c + vdot(crc, crc);
+    float w_p = fmaf(ii_p, vdot(crp, crp), im_p);
+    float dl = -cn / (w_p + w_c + 1e-6f);
+    v3 P = vscale(n, dl);
+    v3 dp_c = vscale(P, im_c);
+    q4 dq_c = qscale(vqmul(vcross(rcw, P), s.q), 0.5f);
+    v3 dp_p = vscale(P, -im_p);
+    q4 dq_p = qscale(vqmul(vcross(rpw, P), qp), -0.5f * ii_p);
+    q4 a_p = qmul(qp, M.l4(MBD_F_PQ, c.l));
+    q4 a_c = qmul(s.q, M.l4(MBD_F_JQ, c.l));
+    q4 j = qmul(qconj(a_p), a_c);
+    v3 dqj;
+    const int b0 = MBD_F_DOF0, b1 = MBD_F_DOF0 + MBD_DOF_STRIDE, b2 = MBD_F_DOF0 + 2 * MBD_DOF_STRIDE;
+    if (c.ndof == 1) {
+      float psi, r10, r20;
+      axis_angle_1dof(j, psi, r10, r20);
+      float e0 = psi - clampf(psi, M.lf(b0 + MBD_D_LO, c.l), M.lf(b0 + MBD_D_HI, c.l));
+      dqj = V3(e0, -r20, r10);
+    } else {
+      JointAngles ja;
+      axis_angle_ang(j, M.lf(MBD_F_PARITY, c.l), ja);
+      float e0 = ja.ang[0] - clampf(ja.ang[0], M.lf(b0 + MBD_D_LO, c.l), M.lf(b0 + MBD_D_HI, c.l));
+      float e1 = ja.ang[1] - clampf(ja.ang[1], M.lf(b1 + MBD_D_LO, c.l), M.lf(b1 + MBD_D_HI, c.l));
+      float e2 = ja.ang[2] - clampf(ja.ang[2], M.lf(b2 + MBD_D_LO, c.l), M.lf(b2 + MBD_D_HI, c.l));
+      dqj = vscale(ja.ax[0], e0);
+      dqj = vfma(ja.ax[1], e1, dqj);
+      dqj = vfma(ja.ax[2], e2, dqj);
+    }
+    v3 dq = vrotate(dqj, a_p);
+    float th;
+    v3 na = vnormalize(dq, &th);
+    float nn = vdot(na, na);
+    float dla = -th / (fmaf(ii_p, nn, nn) + 1e-6f);
+    v3 Pa = vscale(na, dla);
+    q4 dqa_c = qscale(vqmul(Pa, s.q), 0.5f);
+    q4 dqa_p = qscale(vqmul(Pa, qp), -0.5f * ii_p);
+    dpc = vscale(dp_c, M.hf(MBD_H_SCALE_POS));
+    dqc = qadd(qscale(dq_c, M.hf(MBD_H_SCALE_POS)), qscale(dqa_c, M.hf(MBD_H_SCALE_ANG)));
+    S.put_e3(c.l, 0, vscale(dp_p, M.hf(MBD_H_SCALE_POS)));
+    S.put_e4(c.l, 3, qadd(qscale(dq_p, M.hf(MBD_H_SCALE_POS)), qscale(dqa_p, M.hf(MBD_H_SCALE_ANG))));
+  }
+  Y.arrive_terms(c.l);
+  Y.phase_end();
+  // ---- D: gather child deltas, apply; contacts; project_xd; contact velocities; publish q,w ----------
+  Y.wait_terms(c.child);
+  {
+    v3 dp = dpc;
+    q4 dq = dqc;
+#pragma unroll
+    for (int k = 0; k < MBD_MAXCHILD; ++k) {
+      if (c.child[k] >= 0) { dp = vadd(dp, S.e3(c.child[k], 0)); dq = qadd(dq, S.e4(c.child[k], 3)); }
+    }
+    s.p = vadd(s.p, dp);
+    s.q = qnormalize(qadd(s.q, dq));
+  }
+  float dlam[MBD_MAXCON];
+  v3 cpos[MBD_MAXCON];
+  const v3 nrm = V3(0.0f, 0.0f, 1.0f);
+  if (c.ncon > 0) {
+    const float im = M.lf(MBD_F_INV_MASS, c.l);
+    v3 dp = V3(0.0f, 0.0f, 0.0f);
+    q4 dq = Q4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int ci = 0; ci < MBD_MAXCON; ++ci) {
+      dlam[ci] = 0.0f; cpos[ci] = V3(0.0f, 0.0f, 0.0f);
+      if (ci < c.ncon) {
+        int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
+        float radius = M.lf(base + 3, c.l), mu = M.lf(base + 4, c.l);
+        v3 centre = vadd(s.p, vrotate(M.l3(base, c.l), s.q));
+        float dist = centre.z - radius;
+        v3 cp = V3(centre.x, centre.y, centre.z - (radius + 0.5f * dist));
+        cpos[ci] = cp;
+        bool coll = dist < 0.0f;
+        v3 r = vsub(cp, s.p);
+        v3 cr = vcross(r, nrm);
+        float w = im + vdot(cr, cr);
+        float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
+        v3 P = vscale(nrm, dl);
+        dp = vadd(dp, vscale(P, im));
+        dq = qadd(dq, qscale(vqmul(vcross(r, P), s.q), 0.5f));
+        v3 rl = vinv_rotate(r, s.q);
+        v3 pbar = vadd(p_prev, vrotate(rl, q_prev));
+        v3 d = vsub(cp, pbar);
+        v3 dt_ = vsub(d, vscale(nrm, vdot(d, nrm)));
+        float ct;
+        v3 nt = vnormalize(dt_, &ct);
+        v3 crt = vcross(r, nt);
+        float wt = im + vdot(crt, crt);
+        float dlt = -ct / (wt + 1e-6f);
+        bool stat = coll && (fabsf(dlt) < mu * fabsf(dl));
+        float dlt_m = stat ? dlt : 0.0f;
+        v3 Pt = vscale(nt, dlt_m);
+        dp = vadd(dp, vscale(Pt, im));
+        dq = qadd(dq, qscale(vqmul(vcross(r, Pt), s.q), 0.5f));
+        dlam[ci] = dl;
+      }
+    }
+    s.p = vfma(dp, M.hf(MBD_H_COLLIDE_SCALE), s.p);
+    s.q = qnormalize(qadd(s.q, qscale(dq, M.hf(MBD_H_COLLIDE_SCALE))));
+  }
+  {
+    s.v = vscale(vsub(s.p, p_prev), M.hf(MBD_H_INV_DT));
+    q4 dq = qmul(s.q, qconj(q_prev));
+    float sc = dq.w >= 0.0f ? M.hf(MBD_H_TWO_INV_DT) : -M.hf(MBD_H_TWO_INV_DT);
+    s.w = V3(dq.x * sc, dq.y * sc, dq.z * sc);
+  }
+  if (c.ncon > 0) {
+    const float im = M.lf(MBD_F_INV_MASS, c.l);
+    v3 dv = V3(0.0f, 0.0f, 0.0f), dw = V3(0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int ci = 0; ci < MBD_MAXCON; ++ci) {
+      if (ci < c.ncon) {
+        int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
+        float mu = M.lf(base + 4, c.l);
+        float dl = dlam[ci];
+        v3 r = vsub(cpos[ci], s.p);
+        v3 rel = vadd(s.v, vcross(s.w, r));
+        float vn = vdot(rel, nrm);
+        v3 vt = vsub(rel, vscale(nrm, vn));
+        float vtn;
+        v3 vtd = vnormalize(vt, &vtn);
+        float fr = mu * fabsf(dl) * M.hf(MBD_H_INV_DT);
+        float mag = fr < vtn ? fr : vtn;
+        v3 dvel = vscale(vtd, -mag);
+        v3 crd = vcross(r, vtd);
+        float wd = im + vdot(crd, crd);
+        v3 p_dyn = vscale(dvel, 1.0f / (wd + 1e-6f));
+        v3 rel_old = vadd(v_before, vcross(w_before, r));
+        float vn_old = vdot(rel_old, nrm);
+        float rest = -M.hf(MBD_H_ELASTICITY) * vn_old;
+        rest = rest < 0.0f ? rest : 0.0f;
+        v3 dv_rest = vscale(nrm, -vn + rest);
+        v3 crn = vcross(r, nrm);
+        float wn = im + vdot(crn, crn);
+        v3 p_rest = vscale(dv_rest, 1.0f / (wn + 1e-6f));
+        bool sinking = vn_old <= 0.0f;
+        v3 P = p_dyn;
+        if (sinking) P = vadd(P, p_rest);
+        if (dl == 0.0f) P = V3(0.0f, 0.0f, 0.0f);
+        dv = vadd(dv, vscale(P, im));
+        dw = vadd(dw, vcross(r, P));
+      }
+    }
+    s.v = vadd(s.v, dv);
+    s.w = vadd(s.w, dw);
+  }
+  S.put_q(c.l, s.q);
+  S.put_w(c.l, s.w);
+  Y.arrive_pose(c.l);
+  Y.phase_end();
+}
+
+__device__ __forceinline__ v3 link_origin_w(const ModelSmem& M, int l, const LinkState& s) {
+  return vsub(s.p, vrotate(M.l3(MBD_F_COM, l), s.q));
+}
+__device__ __forceinline__ v3 link_origin_vel_w(const ModelSmem& M, int l, const LinkState& s) {
+  v3 rc = vrotate(M.l3(MBD_F_COM, l), s.q);
+  return vadd(s.v, vcross(rc, s.w));
+}
+
+}  // namespace mbd

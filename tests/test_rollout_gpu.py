@@ -33,10 +33,17 @@ def _actions(rng, n, H, nu, scale=0.88):
     return np.clip(rng.normal(size=(n, H, nu)) * scale, -1, 1).astype(np.float32)
 
 
+@pytest.fixture(params=[1, 2, 3, 4], ids=["v1-lane-per-link", "v2-cta-bar", "v2-named-bar", "v2-mbarrier"])
+def variant(request):
+    ops.set_kernel_variant(request.param)
+    yield request.param
+    ops.set_kernel_variant(0)
+
+
 @pytest.mark.parametrize("n,H,nsub", [(1, 1, 1), (8, 1, 1), (5, 2, 3), (8, 1, 7), (37, 5, 0), (64, 50, 0), (129, 7, 0)])
-def test_humanoidrun_rollout_bit_exact(orc, hr, n, H, nsub):
+def test_humanoidrun_rollout_bit_exact(orc, hr, variant, n, H, nsub):
     """per physics step (nsub=1), per env step (H=1) and per rollout; ragged n (not a multiple
-    of the 8 samples per CTA), n=1."""
+    of the samples per CTA), n=1 — for every kernel mapping."""
     env, blob, st, m = hr
     Y = _actions(np.random.default_rng(n * 100 + H), n, H, 17)
     ref = orc.xpbd_rollout(blob, st, Y, want_rewss=True, want_final=True, nsub_override=nsub)
@@ -46,7 +53,7 @@ def test_humanoidrun_rollout_bit_exact(orc, hr, n, H, nsub):
     assert_bit_exact(N(out["rews"]), ref["rews"], "rews")
 
 
-def test_humanoidrun_saturated_and_zero_actions(orc, hr):
+def test_humanoidrun_saturated_and_zero_actions(orc, hr, variant):
     env, blob, st, m = hr
     Y = np.zeros((24, 50, 17), np.float32)
     Y[8:16] = 1.0; Y[16:] = -1.0
@@ -58,7 +65,7 @@ def test_humanoidrun_saturated_and_zero_actions(orc, hr):
     assert np.isfinite(ref["final"]).all()
 
 
-def test_humanoidrun_golden_fixture(hr):
+def test_humanoidrun_golden_fixture(hr, variant):
     """the committed oracle fixture (does not need the oracle library at run time)"""
     env, blob, st, m = hr
     g = np.load(os.path.join(G, "humanoidrun_oracle.npz"))
@@ -81,7 +88,7 @@ def test_sampling_bit_exact(orc):
     assert abs(N(got)).max() <= 1.0
 
 
-def test_fused_sample_rollout_equals_two_step_and_oracle(orc, hr):
+def test_fused_sample_rollout_equals_two_step_and_oracle(orc, hr, variant):
     env, blob, st, m = hr
     key = np.uint32([5, 6]); n_total, n_begin, n_local, H = 4096, 1024, 72, 50
     Ybar = (np.random.default_rng(2).normal(size=850) * 0.1).astype(np.float32)
@@ -94,7 +101,7 @@ def test_fused_sample_rollout_equals_two_step_and_oracle(orc, hr):
     assert_bit_exact(N(two["rews"]), N(rews))
 
 
-def test_humanoidtrack_demo_bit_exact(orc):
+def test_humanoidtrack_demo_bit_exact(orc, variant):
     env = mbd_b200.envs.get_env("humanoidtrack")
     st = env.reset(None).pipeline_state.raw
     m = env.device_model(torch.device(DEV))
@@ -133,7 +140,7 @@ def test_car2d_bit_exact(orc):
     assert_bit_exact(N(out["rews"]), orc.car2d_rollout(car.params, car.x0, refY.reshape(n, H, 2))["rews"])
 
 
-def test_full_size_properties(orc, hr):
+def test_full_size_properties(orc, hr, variant):
     """BASELINE size (8192 x 50): oracle-checked slice + size-independent properties."""
     env, blob, st, m = hr
     key = np.uint32([1, 2]); n, H = 8192, 50
