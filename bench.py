@@ -42,15 +42,19 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _ncu_traffic():
-    """per-launch DRAM bytes of the rollout kernel from the committed ncu --set full capture."""
+def _ncu_summary():
+    """numbers of the rollout kernel from the committed ncu --set full capture (profiles/)."""
     p = os.path.join(ROOT, "profiles", "rollout_kernel_summary.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            return json.load(open(p))
         except Exception:  # noqa: BLE001
-            return None
-    return None
+            return {}
+    return {}
+
+
+def _ncu_traffic():
+    return _ncu_summary().get("dram_bytes_per_launch")
 
 
 class ClockSampler:
@@ -252,6 +256,15 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_s * 1e3,
                          "note": "path is fp32-issue bound, not HBM bound (SURVEY F7): see DESIGN.md roofline section"},
         }
+        # the roofline that actually binds: warp-instruction issue slots.
+        # instructions per launch come from the committed ncu capture of the same kernel/workload.
+        wi = _ncu_summary().get("warp_instructions")
+        if wi and e.n_local == NSAMPLE:
+            clk = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_issue = 148 * 4 * clk * 1e6  # 1 warp-instruction per SM sub-partition per cycle
+            line["roofline_issue"] = {"bound": "fp32 issue slots", "achieved": wi / kern_s, "peak": peak_issue, "unit": "warp-inst/s",
+                                      "frac": wi / kern_s / peak_issue, "warp_instructions_per_launch": wi,
+                                      "source": "profiles/rollout_kernel_summary.json (ncu smsp__inst_executed.sum)"}
         if world == 1 and not args.no_cpu_baseline:
             val, tcpu, threads = time_cpu_oracle(args.cpu_samples, 3, 1)
             line["cpu_baseline"] = {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",

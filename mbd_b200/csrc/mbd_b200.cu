@@ -515,17 +515,36 @@ __global__ void k_wsum_runs(const float* __restrict__ w, const float* __restrict
   for (int n = n0 + 1; n < n1; ++n) acc = fmaf(w[n], Y[(size_t)n * HNu + j], acc);
   runs[(size_t)r * HNu + j] = acc;
 }
-// pairwise (adjacent) tree over `count` rows of [count][HNu] -> out[HNu]; binary-counter stack
+// pairwise (adjacent) tree over `count` rows of [count][stride] -> value for column j; binary-counter
+// stack.  Aligned blocks of 8 rows are loaded together (8 loads in flight) and folded in registers in the
+// same adjacent-pair order, then pushed at level 3 — identical association, 8x fewer serialized loads.
 __device__ __forceinline__ float tree_sum_rows(const float* __restrict__ rows, int count, int stride, int j) {
   float stack[32];
   int depth = 0;
-  for (int r = 0; r < count; ++r) {
-    float v = rows[(size_t)r * stride + j];
-    int rr = r;
-    while (rr & 1) { v = stack[--depth] + v; rr >>= 1; }
+  int r = 0;
+  for (; r + 8 <= count; r += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = rows[(size_t)(r + k) * stride + j];
+    float b = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    int rr = r >> 3;
+    while (rr & 1) { b = stack[--depth] + b; rr >>= 1; }
+    stack[depth++] = b;
+  }
+  if (r < count) {
+    // ragged tail (< 8 rows): plain binary counter over single rows, then merged as ONE block below
+    float tstack[4];
+    int td = 0;
+    for (int q = 0; r + q < count; ++q) {
+      float v = rows[(size_t)(r + q) * stride + j];
+      int rr = q;
+      while (rr & 1) { v = tstack[--td] + v; rr >>= 1; }
+      tstack[td++] = v;
+    }
+    float v = tstack[--td];
+    while (td > 0) v = tstack[--td] + v;
     stack[depth++] = v;
   }
-  // fold leftovers (count not a power of two): right-to-left
   float v = stack[--depth];
   while (depth > 0) v = stack[--depth] + v;
   return v;
