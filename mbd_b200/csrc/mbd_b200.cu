@@ -92,6 +92,9 @@ struct RolloutArgs {
   int n_total, n_begin;
   float sigma;
   const float* Ybar;       // [H*nu]
+  // v2 mapping: link owned by (warp, half) and the half-warp offset (in units of 4 lanes) of every link's row
+  signed char wl[MBD_MAXL][2];
+  unsigned long long offs;
 };
 
 template <bool FUSED>
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
 }
 
 // ---- v2 rollout kernel: warp per link, lane per sample (xpbd_wpl.cuh) -------------------------------------
-template <bool FUSED, int NWARPS, int MINB, int SYNC>
+template <bool FUSED, int NWARPS, int MINB, int SYNC, int SPLIT>
 __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a) {
   __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
   __shared__ __align__(8) uint64_t mbar;
@@ -238,18 +241,23 @@ __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a
   ModelSmem M;
   M.f = sblob;
 
-  const int tid = threadIdx.x, lane = tid & 31, l = tid >> 5;  // warp = link
+  static_assert(SPLIT == 1 || SPLIT == 2, "links per warp");
+  static_assert(SPLIT == 1 || SYNC == 0, "edge barriers assume one link per warp");
+  constexpr int kLpl = kWplLanes / SPLIT;                      // lanes (= samples) per link
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int l = a.wl[tid >> 5][SPLIT == 1 ? 0 : lane / kLpl];  // warp (and half) -> link
+  const int slot = lane % kLpl;                                // sample index inside the CTA
   const int L = M.hi(MBD_H_NLINK), nu = M.hi(MBD_H_NU);
   const int HNu = a.H * nu;
   const int nsub = a.nsub_override > 0 ? a.nsub_override : M.hi(MBD_H_NFRAMES);
   const int reward_kind = M.hi(MBD_H_REWARD);
   const int ntrack = M.hi(MBD_H_NTRACK);
-  const int nthreads = 32 * L;
+  const int nthreads = blockDim.x;
 
   if (FUSED) {
     const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
-    const int first = blockIdx.x * kWplLanes;
-    const int cnt = min(kWplLanes, a.n - first) * HNu;
+    const int first = blockIdx.x * kLpl;
+    const int cnt = min(kLpl, a.n - first) * HNu;
     for (int e = tid; e < cnt; e += nthreads) {
       int ns = first + e / HNu, j = e % HNu;
       uint32_t idx = (uint32_t)(a.n_begin + ns) * (uint32_t)HNu + (uint32_t)j;
@@ -261,13 +269,18 @@ __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a
   WplSmem S;
   S.X = dyn;
   S.E = dyn + L * kXF * kWplLanes;
-  S.lane = lane;
+  S.lane = slot;
+  S.offs = a.offs;
+  // a thread whose half owns no link (odd link count) shadows its partner's link into the unused half of
+  // that row: it executes the same code, nobody reads what it writes, and it produces no output
+  const bool owner = (S.off(l) == (lane / kLpl) * kLpl);
+  if (!owner) S.offs = (S.offs & ~(0xFull << (4 * l))) | ((unsigned long long)(((lane / kLpl) * kLpl) >> 2) << (4 * l));
   WarpCfg c;
   load_warp_cfg(M, l, c);
 
-  const int n_local = blockIdx.x * kWplLanes + lane;
-  const bool active = n_local < a.n;
-  const int n_rd = active ? n_local : a.n - 1;
+  const int n_local = blockIdx.x * kLpl + slot;
+  const bool active = n_local < a.n && owner;
+  const int n_rd = n_local < a.n ? n_local : a.n - 1;
 
   LinkState s;
   {
@@ -348,11 +361,11 @@ __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a
   if (a.logpd && a.xref) {
     // per-body accumulators -> shared (reuse E), summed in track order by warp 0
     __syncthreads();  // every warp is done with E
-    if (my_track >= 0) S.E[my_track * kWplLanes + lane] = tacc;
+    if (my_track >= 0 && owner) S.E[my_track * kWplLanes + slot] = tacc;
     __syncthreads();
     if (l == 0 && active) {
       float tot = 0.0f;
-      for (int k = 0; k < ntrack; ++k) tot += S.E[k * kWplLanes + lane];
+      for (int k = 0; k < ntrack; ++k) tot += S.E[k * kWplLanes + slot];
       a.logpd[n_local] = 0.0f - tot / (float)(ntrack * a.H);
     }
   }
@@ -574,7 +587,72 @@ __global__ void k_update(const float* __restrict__ partials, int P, int HNu, con
 struct mbd_model {
   uint32_t* blob_dev;
   int L, nu, n_frames, ntrack;
+  // v2 kernel mappings (host side): one link per warp, and two same-type links per warp
+  signed char wl1[MBD_MAXL][2], wl2[MBD_MAXL][2];
+  unsigned long long offs1, offs2;
+  int nwarps2;
 };
+
+// Pairs links with the same (ndof, #contacts, has-children) signature so that the two halves of a warp run
+// the same code path (right/left limbs); leftovers are paired jointed-with-jointed, the root stays alone.
+static void build_pairing(mbd_model* m, const uint32_t* blob) {
+  const int32_t* bi = reinterpret_cast<const int32_t*>(blob);
+  auto li = [&](int f, int l) { return bi[MBD_HDR_WORDS + f * MBD_MAXL + l]; };
+  const int L = m->L;
+  int sig[MBD_MAXL];
+  bool used[MBD_MAXL] = {false};
+  for (int l = 0; l < L; ++l) sig[l] = li(MBD_F_NDOF, l) * 64 + li(MBD_F_NCON, l) * 4 + (li(MBD_F_CHILD0, l) >= 0 ? 1 : 0);
+  m->offs1 = 0; m->offs2 = 0; m->nwarps2 = 0;
+  for (int l = 0; l < MBD_MAXL; ++l) { m->wl1[l][0] = (signed char)(l < L ? l : 0); m->wl1[l][1] = m->wl1[l][0]; m->wl2[l][0] = m->wl2[l][1] = 0; }
+  {
+    // One link per warp: warps are issued by SM sub-partition (warp id % 4).  Spread the joint work
+    // (weight ~ ndof) evenly over the four schedulers and keep links with contacts on different ones
+    // (longest-processing-time greedy; slot s of scheduler q is warp 4*s + q).
+    int order[MBD_MAXL], nslot[4] = {0, 0, 0, 0};
+    float load[4] = {0, 0, 0, 0}, conload[4] = {0, 0, 0, 0};
+    int cap[4];
+    for (int q = 0; q < 4; ++q) cap[q] = (L - q + 3) / 4;
+    auto weight = [&](int l) { int nd = li(MBD_F_NDOF, l); return nd <= 0 ? 0.0f : (nd == 1 ? 0.6f : (nd == 2 ? 0.93f : 1.0f)); };
+    for (int l = 0; l < L; ++l) order[l] = l;
+    for (int i = 0; i < L; ++i)       // sort: contacts first, then by weight, descending (stable)
+      for (int j = i + 1; j < L; ++j) {
+        float wi = weight(order[i]) + 10.0f * li(MBD_F_NCON, order[i]), wj = weight(order[j]) + 10.0f * li(MBD_F_NCON, order[j]);
+        if (wj > wi) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+      }
+    for (int i = 0; i < L; ++i) {
+      int l = order[i], best = -1;
+      for (int q = 0; q < 4; ++q) {
+        if (nslot[q] >= cap[q]) continue;
+        float cost = load[q] + 100.0f * (li(MBD_F_NCON, l) > 0 ? conload[q] : 0.0f);
+        if (best < 0 || cost < load[best] + 100.0f * (li(MBD_F_NCON, l) > 0 ? conload[best] : 0.0f)) best = q;
+      }
+      int w = 4 * nslot[best] + best;
+      m->wl1[w][0] = m->wl1[w][1] = (signed char)l;
+      nslot[best]++; load[best] += weight(l); conload[best] += li(MBD_F_NCON, l) > 0 ? 1.0f : 0.0f;
+    }
+  }
+  auto add_pair = [&](int a, int b) {
+    int w = m->nwarps2++;
+    m->wl2[w][0] = (signed char)a;
+    m->wl2[w][1] = (signed char)(b >= 0 ? b : a);
+    if (b >= 0) m->offs2 |= (unsigned long long)(16 >> 2) << (4 * b);
+    used[a] = true;
+    if (b >= 0) used[b] = true;
+  };
+  for (int a = 0; a < L; ++a) {
+    if (used[a]) continue;
+    for (int b = a + 1; b < L; ++b)
+      if (!used[b] && sig[b] == sig[a]) { add_pair(a, b); break; }
+  }
+  int prev = -1;
+  for (int a = 0; a < L; ++a) {  // leftovers: jointed with jointed
+    if (used[a] || li(MBD_F_NDOF, a) <= 0) continue;
+    if (prev < 0) prev = a; else { add_pair(prev, a); prev = -1; }
+  }
+  if (prev >= 0) add_pair(prev, -1);
+  for (int a = 0; a < L; ++a)
+    if (!used[a]) add_pair(a, -1);
+}
 
 static int g_kernel_variant = 0;  // 0 = auto, 1 = v1 (lane per link), 2..4 = v2 (warp per link; CTA / named / mbarrier sync)
 static thread_local char g_err[256] = "";
@@ -599,7 +677,7 @@ int mbd_device_count(void) {
 }
 
 int mbd_set_kernel_variant(int v) {
-  if (v < 0 || v > 4) return MBD_EINVAL;
+  if (v < 0 || v > 5) return MBD_EINVAL;
   g_kernel_variant = v;
   return MBD_OK;
 }
@@ -627,6 +705,7 @@ mbd_model* mbd_model_create(const uint32_t* blob_host, size_t nwords) {
   const int32_t* hi = reinterpret_cast<const int32_t*>(blob_host);
   m->L = hi[MBD_H_NLINK]; m->nu = hi[MBD_H_NU]; m->n_frames = hi[MBD_H_NFRAMES]; m->ntrack = hi[MBD_H_NTRACK];
   if (m->L < 1 || m->L > MBD_MAXL || m->ntrack > MBD_MAXTRACK) { delete m; snprintf(g_err, sizeof(g_err), "bad link count"); return nullptr; }
+  build_pairing(m, blob_host);
   if (cudaMalloc(&m->blob_dev, nwords * 4) != cudaSuccess || cudaMemcpy(m->blob_dev, blob_host, nwords * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "mbd_model_create: cudaMalloc/cudaMemcpy failed");
     delete m;
@@ -652,32 +731,34 @@ int mbd_sample(const uint32_t key[2], int n_total, int n_begin, int n_local, int
   return MBD_OK;
 }
 
-static int launch_rollout(bool fused, const mbd::RolloutArgs& a, int L, cudaStream_t st) {
+#define MBD_LAUNCH_WPL(NW, MINB, SYNC, SPLIT, GRID, THREADS)                                             \
+  do {                                                                                                 \
+    if (fused)                                                                                         \
+      mbd::k_rollout_wpl<true, NW, MINB, SYNC, SPLIT><<<GRID, THREADS, dyn, st>>>(a);                  \
+    else                                                                                               \
+      mbd::k_rollout_wpl<false, NW, MINB, SYNC, SPLIT><<<GRID, THREADS, dyn, st>>>(a);                 \
+  } while (0)
+
+static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cudaStream_t st) {
+  const int L = m->L;
   int variant = g_kernel_variant;
-  if (variant == 0) variant = (a.n >= 4096 || L != 11) ? 2 : 1;  // small shards: the lane-per-link kernel has more warps in flight
+  // auto: small shards keep more warps in flight with the lane-per-link kernel; large ones use v2
+  if (variant == 0) variant = (L == 11) ? (a.n >= 2048 ? 3 : 1) : 2;
   if (variant >= 2) {
-    int grid = (a.n + mbd::kWplLanes - 1) / mbd::kWplLanes;
     size_t dyn = (size_t)L * (mbd::kXF + mbd::kEF) * mbd::kWplLanes * sizeof(float);
-    if (L == 11 && variant == 3) {  // named edge barriers (shorter chain, best for 1 CTA/SM)
-      if (fused)
-        mbd::k_rollout_wpl<true, 11, 2, 2><<<grid, 32 * L, dyn, st>>>(a);
-      else
-        mbd::k_rollout_wpl<false, 11, 2, 2><<<grid, 32 * L, dyn, st>>>(a);
-    } else if (L == 11 && variant == 2) {  // the humanoids: 352 threads, 2 CTAs/SM (<= 88 registers), CTA-wide barriers
-      if (fused)
-        mbd::k_rollout_wpl<true, 11, 2, 0><<<grid, 32 * L, dyn, st>>>(a);
-      else
-        mbd::k_rollout_wpl<false, 11, 2, 0><<<grid, 32 * L, dyn, st>>>(a);
-    } else if (L == 11 && variant == 4) {  // mbarrier point-to-point (polling)
-      if (fused)
-        mbd::k_rollout_wpl<true, 11, 2, 1><<<grid, 32 * L, dyn, st>>>(a);
-      else
-        mbd::k_rollout_wpl<false, 11, 2, 1><<<grid, 32 * L, dyn, st>>>(a);
+    const bool split = (variant == 5);
+    memcpy(a.wl, split ? m->wl2 : m->wl1, sizeof(a.wl));
+    a.offs = split ? m->offs2 : m->offs1;
+    if (split) {
+      int grid = (a.n + 15) / 16, nw = m->nwarps2;
+      if (nw <= 6) MBD_LAUNCH_WPL(6, 4, 0, 2, grid, 32 * nw);     // humanoids: 6 warps, 4 CTAs/SM
+      else MBD_LAUNCH_WPL(MBD_MAXL, 1, 0, 2, grid, 32 * nw);
     } else {
-      if (fused)
-        mbd::k_rollout_wpl<true, MBD_MAXL, 1, 0><<<grid, 32 * L, dyn, st>>>(a);
-      else
-        mbd::k_rollout_wpl<false, MBD_MAXL, 1, 0><<<grid, 32 * L, dyn, st>>>(a);
+      int grid = (a.n + mbd::kWplLanes - 1) / mbd::kWplLanes;
+      if (L == 11 && variant == 2) MBD_LAUNCH_WPL(11, 2, 0, 1, grid, 32 * L);       // CTA-wide barriers
+      else if (L == 11 && variant == 3) MBD_LAUNCH_WPL(11, 2, 2, 1, grid, 32 * L);  // named edge barriers
+      else if (L == 11 && variant == 4) MBD_LAUNCH_WPL(11, 2, 1, 1, grid, 32 * L);  // mbarrier point-to-point
+      else MBD_LAUNCH_WPL(MBD_MAXL, 1, 0, 1, grid, 32 * L);
     }
   } else {
     int grid = (a.n + mbd::kSPB - 1) / mbd::kSPB;
@@ -700,7 +781,7 @@ int mbd_rollout(const mbd_model* m, const float* state_init_dev, const float* Y0
   a.blob = m->blob_dev; a.state_init = state_init_dev; a.Y0s = const_cast<float*>(Y0s_dev); a.n = n; a.H = H;
   a.rewss = rewss_dev; a.rews = rews_dev; a.xref = xref_dev; a.href = href; a.logpd = logpd_dev;
   a.final_state = final_state_dev; a.track_pos = track_pos_dev; a.nsub_override = nsub_override;
-  return launch_rollout(false, a, m->L, (cudaStream_t)s);
+  return launch_rollout(false, a, m, (cudaStream_t)s);
 }
 
 int mbd_sample_rollout(const mbd_model* m, const float* state_init_dev, const uint32_t key[2], int n_total, int n_begin, int n_local,
@@ -715,7 +796,7 @@ int mbd_sample_rollout(const mbd_model* m, const float* state_init_dev, const ui
   a.blob = m->blob_dev; a.state_init = state_init_dev; a.Y0s = Y0s_dev; a.n = n_local; a.H = H;
   a.rews = rews_dev; a.xref = xref_dev; a.href = href; a.logpd = logpd_dev;
   a.k0 = key[0]; a.k1 = key[1]; a.n_total = n_total; a.n_begin = n_begin; a.sigma = sigma; a.Ybar = Ybar_dev;
-  return launch_rollout(true, a, m->L, (cudaStream_t)s);
+  return launch_rollout(true, a, m, (cudaStream_t)s);
 }
 
 int mbd_car2d_rollout(const float* params_dev, const float* x0_dev, const uint32_t* key, int n_total, int n_begin, int n_local, int H,

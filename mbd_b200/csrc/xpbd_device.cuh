@@ -95,6 +95,79 @@ struct ModelSmem {
 
 struct LinkState { v3 p; q4 q; v3 w; v3 v; };  // x_i.pos, x_i.rot, xd_i.ang, xd_i.vel
 
+// ---- contact.get (MJX plane_sphere) + collisions.resolve_position / resolve_velocity ----------------
+// Specialised for the ground-plane normal n = +z (the only contact class of the positional envs in scope):
+//   r x n = (r.y, -r.x, 0);   P = dl*n = (0,0,dl);   r x P = (r.y dl, -r.x dl, 0);
+//   tangential vectors have z = 0.  Same formulas as the general XPBD contact with n substituted —
+// the oracle (oracle/mbd_oracle.c::contact_position_plane / contact_velocity_plane) uses the identical
+// expressions.  vqmul_xy is vqmul with a.z = 0.
+__device__ __forceinline__ q4 vqmul_xy(float ax, float ay, q4 q) {
+  return Q4(fmaf(-ay, q.y, -(ax * q.x)), fmaf(ay, q.z, ax * q.w), fmaf(ay, q.w, -(ax * q.z)), fmaf(-ay, q.x, ax * q.y));
+}
+
+// one sphere-plane contact of link l: accumulates the position-level correction (dp, dq); returns dlambda and
+// the contact point for the velocity pass
+__device__ __forceinline__ void contact_position_plane(const ModelSmem& M, int l, int ci, float im, v3 p, q4 q, v3 p_prev, q4 q_prev,
+                                                       v3& dp, q4& dq, float& dl_out, v3& cp_out) {
+  const int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
+  const float radius = M.lf(base + 3, l), mu = M.lf(base + 4, l);
+  v3 centre = vadd(p, vrotate(M.l3(base, l), q));
+  float dist = centre.z - radius;
+  v3 cp = V3(centre.x, centre.y, centre.z - (radius + 0.5f * dist));  // pos = c - n (r + dist/2)
+  bool coll = dist < 0.0f;
+  v3 r = vsub(cp, p);
+  float w = im + fmaf(r.x, r.x, r.y * r.y);
+  float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
+  dp.z = dp.z + dl * im;
+  dq = qadd(dq, qscale(vqmul_xy(r.y * dl, -(r.x * dl), q), 0.5f));
+  // static friction: cancel the tangential travel of the contact point since x_i_prev
+  v3 rl = vinv_rotate(r, q);
+  v3 pbar = vadd(p_prev, vrotate(rl, q_prev));
+  float dx = cp.x - pbar.x, dy = cp.y - pbar.y;
+  float ct = sqrtf(fmaf(dy, dy, dx * dx));
+  float inv = (ct == 0.0f) ? 0.0f : 1.0f / ct;
+  float ntx = dx * inv, nty = dy * inv;
+  float c1 = -(r.z * nty), c2 = r.z * ntx, c3 = fmaf(r.x, nty, -(r.y * ntx));
+  float wt = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
+  float dlt = -ct / (wt + 1e-6f);
+  bool stat = coll && (fabsf(dlt) < mu * fabsf(dl));
+  float m = stat ? dlt : 0.0f;
+  float ptx = ntx * m, pty = nty * m;
+  dp.x = dp.x + ptx * im;
+  dp.y = dp.y + pty * im;
+  dq = qadd(dq, qscale(vqmul(V3(-(r.z * pty), r.z * ptx, fmaf(r.x, pty, -(r.y * ptx))), q), 0.5f));
+  dl_out = dl;
+  cp_out = cp;
+}
+
+__device__ __forceinline__ void contact_velocity_plane(const ModelSmem& M, int l, int ci, float im, float inv_dt, float elasticity, v3 p,
+                                                       v3 v, v3 w, v3 v_before, v3 w_before, v3 cp, float dl, v3& dv, v3& dw) {
+  const float mu = M.lf(MBD_F_CON0 + ci * MBD_CON_STRIDE + 4, l);
+  v3 r = vsub(cp, p);
+  v3 rel = vadd(v, vcross(w, r));
+  float vn = rel.z;
+  float vtn = sqrtf(fmaf(rel.y, rel.y, rel.x * rel.x));
+  float inv = (vtn == 0.0f) ? 0.0f : 1.0f / vtn;
+  float tdx = rel.x * inv, tdy = rel.y * inv;
+  float fr = mu * fabsf(dl) * inv_dt;
+  float mag = fr < vtn ? fr : vtn;
+  float c1 = -(r.z * tdy), c2 = r.z * tdx, c3 = fmaf(r.x, tdy, -(r.y * tdx));
+  float wd = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
+  float kd = 1.0f / (wd + 1e-6f);
+  float pdx = (tdx * -mag) * kd, pdy = (tdy * -mag) * kd;
+  v3 rel_old = vadd(v_before, vcross(w_before, r));
+  float vn_old = rel_old.z;
+  float rest = -elasticity * vn_old;
+  rest = rest < 0.0f ? rest : 0.0f;
+  float wn = im + fmaf(r.x, r.x, r.y * r.y);
+  float prz = (-vn + rest) * (1.0f / (wn + 1e-6f));
+  v3 P = V3(pdx, pdy, (vn_old <= 0.0f) ? prz : 0.0f);
+  if (dl == 0.0f) P = V3(0.0f, 0.0f, 0.0f);
+  dv = vadd(dv, vscale(P, im));
+  dw = vadd(dw, vcross(r, P));
+}
+
+
 struct JointAngles { float ang[3]; v3 ax[3]; float r10, r20; };
 
 // kinematics.axis_angle_ang restated — see oracle/mbd_oracle.c::axis_angle_ang
@@ -285,45 +358,14 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
   v3 cpos[MBD_MAXCON];
 #pragma unroll
   for (int ci = 0; ci < MBD_MAXCON; ++ci) { dlam[ci] = 0.0f; cpos[ci] = V3(0.0f, 0.0f, 0.0f); }
-  const v3 nrm = V3(0.0f, 0.0f, 1.0f);
   if (c.ncon > 0) {
-    const float im = c.inv_mass;
     v3 dp = V3(0.0f, 0.0f, 0.0f);
     q4 dq = Q4(0.0f, 0.0f, 0.0f, 0.0f);
+    const v3 p0 = s.p;
+    const q4 q0 = s.q;
 #pragma unroll
-    for (int ci = 0; ci < MBD_MAXCON; ++ci) {
-      if (ci < c.ncon) {
-        int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
-        float radius = M.lf(base + 3, c.l), mu = M.lf(base + 4, c.l);
-        v3 centre = vadd(s.p, vrotate(M.l3(base, c.l), s.q));
-        float dist = centre.z - radius;
-        v3 cp = V3(centre.x, centre.y, centre.z - (radius + 0.5f * dist));
-        cpos[ci] = cp;
-        bool coll = dist < 0.0f;
-        v3 r = vsub(cp, s.p);
-        v3 cr = vcross(r, nrm);
-        float w = im + vdot(cr, cr);
-        float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
-        v3 P = vscale(nrm, dl);
-        dp = vadd(dp, vscale(P, im));
-        dq = qadd(dq, qscale(vqmul(vcross(r, P), s.q), 0.5f));
-        v3 rl = vinv_rotate(r, s.q);
-        v3 pbar = vadd(prev.p, vrotate(rl, prev.q));
-        v3 d = vsub(cp, pbar);
-        v3 dt_ = vsub(d, vscale(nrm, vdot(d, nrm)));
-        float ct;
-        v3 nt = vnormalize(dt_, &ct);
-        v3 crt = vcross(r, nt);
-        float wt = im + vdot(crt, crt);
-        float dlt = -ct / (wt + 1e-6f);
-        bool stat = coll && (fabsf(dlt) < mu * fabsf(dl));
-        float dlt_m = stat ? dlt : 0.0f;
-        v3 Pt = vscale(nt, dlt_m);
-        dp = vadd(dp, vscale(Pt, im));
-        dq = qadd(dq, qscale(vqmul(vcross(r, Pt), s.q), 0.5f));
-        dlam[ci] = dl;
-      }
-    }
+    for (int ci = 0; ci < MBD_MAXCON; ++ci)
+      if (ci < c.ncon) contact_position_plane(M, c.l, ci, c.inv_mass, p0, q0, prev.p, prev.q, dp, dq, dlam[ci], cpos[ci]);
     s.p = vfma(dp, K.collide_scale, s.p);
     s.q = qnormalize(qadd(s.q, qscale(dq, K.collide_scale)));
   }
@@ -336,42 +378,12 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
   }
   // ---- collisions.resolve_velocity -------------------------------------------------------------------
   if (c.ncon > 0) {
-    const float im = c.inv_mass;
     v3 dv = V3(0.0f, 0.0f, 0.0f), dw = V3(0.0f, 0.0f, 0.0f);
+    const v3 v0 = s.v, w0 = s.w;
 #pragma unroll
-    for (int ci = 0; ci < MBD_MAXCON; ++ci) {
-      if (ci < c.ncon) {
-        int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
-        float mu = M.lf(base + 4, c.l);
-        float dl = dlam[ci];
-        v3 r = vsub(cpos[ci], s.p);
-        v3 rel = vadd(s.v, vcross(s.w, r));
-        float vn = vdot(rel, nrm);
-        v3 vt = vsub(rel, vscale(nrm, vn));
-        float vtn;
-        v3 vtd = vnormalize(vt, &vtn);
-        float fr = mu * fabsf(dl) * K.inv_dt;
-        float mag = fr < vtn ? fr : vtn;
-        v3 dvel = vscale(vtd, -mag);
-        v3 crd = vcross(r, vtd);
-        float wd = im + vdot(crd, crd);
-        v3 p_dyn = vscale(dvel, 1.0f / (wd + 1e-6f));
-        v3 rel_old = vadd(v_before, vcross(w_before, r));
-        float vn_old = vdot(rel_old, nrm);
-        float rest = -K.elasticity * vn_old;
-        rest = rest < 0.0f ? rest : 0.0f;
-        v3 dv_rest = vscale(nrm, -vn + rest);
-        v3 crn = vcross(r, nrm);
-        float wn = im + vdot(crn, crn);
-        v3 p_rest = vscale(dv_rest, 1.0f / (wn + 1e-6f));
-        bool sinking = vn_old <= 0.0f;
-        v3 P = p_dyn;
-        if (sinking) P = vadd(P, p_rest);
-        if (dl == 0.0f) P = V3(0.0f, 0.0f, 0.0f);
-        dv = vadd(dv, vscale(P, im));
-        dw = vadd(dw, vcross(r, P));
-      }
-    }
+    for (int ci = 0; ci < MBD_MAXCON; ++ci)
+      if (ci < c.ncon)
+        contact_velocity_plane(M, c.l, ci, c.inv_mass, K.inv_dt, K.elasticity, s.p, v0, w0, v_before, w_before, cpos[ci], dlam[ci], dv, dw);
     s.v = vadd(s.v, dv);
     s.w = vadd(s.w, dw);
   }

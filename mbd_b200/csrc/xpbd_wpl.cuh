@@ -27,9 +27,13 @@ constexpr int kEF = 7;   // exchange fields per link: T(3)  |  dpp(3) dqp(4)
 struct WplSmem {
   float* X;  // [L][kXF][32]
   float* E;  // [L][kEF][32]
-  int lane;
-  __device__ __forceinline__ float& x(int link, int f) const { return X[(link * kXF + f) * kWplLanes + lane]; }
-  __device__ __forceinline__ float& e(int link, int f) const { return E[(link * kEF + f) * kWplLanes + lane]; }
+  int lane;  // sample slot inside a row, WITHOUT the half-warp offset of the row's owner
+  // Row of link k holds its samples at [off(k) + lane]; off(k) = 0 when a warp owns one link (SPLIT 1) or
+  // 16 * (half of the warp that owns k) when two links share a warp (SPLIT 2).  Packed 4 bits per link.
+  unsigned long long offs;
+  __device__ __forceinline__ int off(int link) const { return (int)((offs >> (4 * link)) & 0xFull) << 2; }
+  __device__ __forceinline__ float& x(int link, int f) const { return X[(link * kXF + f) * kWplLanes + off(link) + lane]; }
+  __device__ __forceinline__ float& e(int link, int f) const { return E[(link * kEF + f) * kWplLanes + off(link) + lane]; }
   __device__ __forceinline__ v3 xp(int link) const { return V3(x(link, 0), x(link, 1), x(link, 2)); }
   __device__ __forceinline__ q4 xq(int link) const { return Q4(x(link, 3), x(link, 4), x(link, 5), x(link, 6)); }
   __device__ __forceinline__ v3 xw(int link) const { return V3(x(link, 7), x(link, 8), x(link, 9)); }
@@ -311,45 +315,15 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
   }
   float dlam[MBD_MAXCON];
   v3 cpos[MBD_MAXCON];
-  const v3 nrm = V3(0.0f, 0.0f, 1.0f);
   if (c.ncon > 0) {
-    const float im = M.lf(MBD_F_INV_MASS, c.l);
     v3 dp = V3(0.0f, 0.0f, 0.0f);
     q4 dq = Q4(0.0f, 0.0f, 0.0f, 0.0f);
+    const v3 p0 = s.p;
+    const q4 q0 = s.q;
 #pragma unroll
     for (int ci = 0; ci < MBD_MAXCON; ++ci) {
       dlam[ci] = 0.0f; cpos[ci] = V3(0.0f, 0.0f, 0.0f);
-      if (ci < c.ncon) {
-        int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
-        float radius = M.lf(base + 3, c.l), mu = M.lf(base + 4, c.l);
-        v3 centre = vadd(s.p, vrotate(M.l3(base, c.l), s.q));
-        float dist = centre.z - radius;
-        v3 cp = V3(centre.x, centre.y, centre.z - (radius + 0.5f * dist));
-        cpos[ci] = cp;
-        bool coll = dist < 0.0f;
-        v3 r = vsub(cp, s.p);
-        v3 cr = vcross(r, nrm);
-        float w = im + vdot(cr, cr);
-        float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
-        v3 P = vscale(nrm, dl);
-        dp = vadd(dp, vscale(P, im));
-        dq = qadd(dq, qscale(vqmul(vcross(r, P), s.q), 0.5f));
-        v3 rl = vinv_rotate(r, s.q);
-        v3 pbar = vadd(p_prev, vrotate(rl, q_prev));
-        v3 d = vsub(cp, pbar);
-        v3 dt_ = vsub(d, vscale(nrm, vdot(d, nrm)));
-        float ct;
-        v3 nt = vnormalize(dt_, &ct);
-        v3 crt = vcross(r, nt);
-        float wt = im + vdot(crt, crt);
-        float dlt = -ct / (wt + 1e-6f);
-        bool stat = coll && (fabsf(dlt) < mu * fabsf(dl));
-        float dlt_m = stat ? dlt : 0.0f;
-        v3 Pt = vscale(nt, dlt_m);
-        dp = vadd(dp, vscale(Pt, im));
-        dq = qadd(dq, qscale(vqmul(vcross(r, Pt), s.q), 0.5f));
-        dlam[ci] = dl;
-      }
+      if (ci < c.ncon) contact_position_plane(M, c.l, ci, M.lf(MBD_F_INV_MASS, c.l), p0, q0, p_prev, q_prev, dp, dq, dlam[ci], cpos[ci]);
     }
     s.p = vfma(dp, M.hf(MBD_H_COLLIDE_SCALE), s.p);
     s.q = qnormalize(qadd(s.q, qscale(dq, M.hf(MBD_H_COLLIDE_SCALE))));
@@ -361,42 +335,13 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     s.w = V3(dq.x * sc, dq.y * sc, dq.z * sc);
   }
   if (c.ncon > 0) {
-    const float im = M.lf(MBD_F_INV_MASS, c.l);
     v3 dv = V3(0.0f, 0.0f, 0.0f), dw = V3(0.0f, 0.0f, 0.0f);
+    const v3 v0 = s.v, w0 = s.w;
 #pragma unroll
-    for (int ci = 0; ci < MBD_MAXCON; ++ci) {
-      if (ci < c.ncon) {
-        int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
-        float mu = M.lf(base + 4, c.l);
-        float dl = dlam[ci];
-        v3 r = vsub(cpos[ci], s.p);
-        v3 rel = vadd(s.v, vcross(s.w, r));
-        float vn = vdot(rel, nrm);
-        v3 vt = vsub(rel, vscale(nrm, vn));
-        float vtn;
-        v3 vtd = vnormalize(vt, &vtn);
-        float fr = mu * fabsf(dl) * M.hf(MBD_H_INV_DT);
-        float mag = fr < vtn ? fr : vtn;
-        v3 dvel = vscale(vtd, -mag);
-        v3 crd = vcross(r, vtd);
-        float wd = im + vdot(crd, crd);
-        v3 p_dyn = vscale(dvel, 1.0f / (wd + 1e-6f));
-        v3 rel_old = vadd(v_before, vcross(w_before, r));
-        float vn_old = vdot(rel_old, nrm);
-        float rest = -M.hf(MBD_H_ELASTICITY) * vn_old;
-        rest = rest < 0.0f ? rest : 0.0f;
-        v3 dv_rest = vscale(nrm, -vn + rest);
-        v3 crn = vcross(r, nrm);
-        float wn = im + vdot(crn, crn);
-        v3 p_rest = vscale(dv_rest, 1.0f / (wn + 1e-6f));
-        bool sinking = vn_old <= 0.0f;
-        v3 P = p_dyn;
-        if (sinking) P = vadd(P, p_rest);
-        if (dl == 0.0f) P = V3(0.0f, 0.0f, 0.0f);
-        dv = vadd(dv, vscale(P, im));
-        dw = vadd(dw, vcross(r, P));
-      }
-    }
+    for (int ci = 0; ci < MBD_MAXCON; ++ci)
+      if (ci < c.ncon)
+        contact_velocity_plane(M, c.l, ci, M.lf(MBD_F_INV_MASS, c.l), M.hf(MBD_H_INV_DT), M.hf(MBD_H_ELASTICITY), s.p, v0, w0, v_before,
+                               w_before, cpos[ci], dlam[ci], dv, dw);
     s.v = vadd(s.v, dv);
     s.w = vadd(s.w, dw);
   }

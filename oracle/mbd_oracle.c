@@ -167,6 +167,75 @@ static inline void axis_angle_ang(q4 j, float parity, JointAngles* o) {
   o->ax[2] = V3(parity * r02, parity * r12, parity * r22);
 }
 
+
+/* ---- contact.get (MJX plane_sphere) + collisions.resolve_position / resolve_velocity -----------------
+ * Written for the ground-plane normal n = +z, the only contact class of the positional envs in
+ * scope (every vendored model collides spheres/capsule caps with the z = 0 floor): with n
+ * substituted, r x n = (r.y, -r.x, 0), P = dl n = (0,0,dl), r x P = (r.y dl, -r.x dl, 0) and
+ * tangential vectors have z = 0.  Same XPBD contact as the general formulation
+ * (brax/positional/collisions.py), term for term. */
+static inline q4 vqmul_xy(float ax, float ay, q4 q) {
+  return Q4(fmaf(-ay, q.y, -(ax * q.x)), fmaf(ay, q.z, ax * q.w), fmaf(ay, q.w, -(ax * q.z)), fmaf(-ay, q.x, ax * q.y));
+}
+static inline void contact_position_plane(const Model* m, int l, int ci, float im, v3 p, q4 q, v3 p_prev, q4 q_prev, v3* dp, q4* dq,
+                                          float* dl_out, v3* cp_out) {
+  const int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
+  const float radius = LFf(m, base + 3, l), mu = LFf(m, base + 4, l);
+  v3 centre = vadd(p, vrotate(LF3(m, base, l), q));
+  float dist = centre.z - radius;                                       /* dist = (c - plane).n - r */
+  v3 cp = V3(centre.x, centre.y, centre.z - (radius + 0.5f * dist));    /* pos = c - n (r + dist/2) */
+  int coll = dist < 0.0f;
+  v3 r = vsub(cp, p);
+  float w = im + fmaf(r.x, r.x, r.y * r.y);                             /* 1/m + |r x n|^2 (identity inertia) */
+  float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
+  dp->z = dp->z + dl * im;
+  *dq = qadd(*dq, qscale(vqmul_xy(r.y * dl, -(r.x * dl), q), 0.5f));
+  /* static friction: cancel the tangential travel of the contact point since x_i_prev */
+  v3 rl = vinv_rotate(r, q);
+  v3 pbar = vadd(p_prev, vrotate(rl, q_prev));
+  float dx = cp.x - pbar.x, dy = cp.y - pbar.y;
+  float ct = sqrtf(fmaf(dy, dy, dx * dx));
+  float inv = (ct == 0.0f) ? 0.0f : 1.0f / ct;
+  float ntx = dx * inv, nty = dy * inv;
+  float c1 = -(r.z * nty), c2 = r.z * ntx, c3 = fmaf(r.x, nty, -(r.y * ntx));
+  float wt = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
+  float dlt = -ct / (wt + 1e-6f);
+  int stat = coll && (fabsf(dlt) < mu * fabsf(dl));
+  float mm = stat ? dlt : 0.0f;
+  float ptx = ntx * mm, pty = nty * mm;
+  dp->x = dp->x + ptx * im;
+  dp->y = dp->y + pty * im;
+  *dq = qadd(*dq, qscale(vqmul(V3(-(r.z * pty), r.z * ptx, fmaf(r.x, pty, -(r.y * ptx))), q), 0.5f));
+  *dl_out = dl;
+  *cp_out = cp;
+}
+static inline void contact_velocity_plane(const Model* m, int l, int ci, float im, v3 p, v3 v, v3 w, v3 v_before, v3 w_before, v3 cp,
+                                          float dl, v3* dv, v3* dw) {
+  const float mu = LFf(m, MBD_F_CON0 + ci * MBD_CON_STRIDE + 4, l);
+  v3 r = vsub(cp, p);
+  v3 rel = vadd(v, vcross(w, r));
+  float vn = rel.z;
+  float vtn = sqrtf(fmaf(rel.y, rel.y, rel.x * rel.x));
+  float inv = (vtn == 0.0f) ? 0.0f : 1.0f / vtn;
+  float tdx = rel.x * inv, tdy = rel.y * inv;
+  float fr = mu * fabsf(dl) * m->inv_dt;                                /* dynamic friction bound mu |dlambda| / dt */
+  float mag = fr < vtn ? fr : vtn;
+  float c1 = -(r.z * tdy), c2 = r.z * tdx, c3 = fmaf(r.x, tdy, -(r.y * tdx));
+  float wd = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
+  float kd = 1.0f / (wd + 1e-6f);
+  float pdx = (tdx * -mag) * kd, pdy = (tdy * -mag) * kd;
+  v3 rel_old = vadd(v_before, vcross(w_before, r));
+  float vn_old = rel_old.z;
+  float rest = -m->elasticity * vn_old;                                 /* restitution: min(-e v_n_old, 0) */
+  rest = rest < 0.0f ? rest : 0.0f;
+  float wn = im + fmaf(r.x, r.x, r.y * r.y);
+  float prz = (-vn + rest) * (1.0f / (wn + 1e-6f));
+  v3 P = V3(pdx, pdy, (vn_old <= 0.0f) ? prz : 0.0f);                   /* "sinking" gate on the normal impulse */
+  if (dl == 0.0f) P = V3(0, 0, 0);
+  *dv = vadd(*dv, vscale(P, im));
+  *dw = vadd(*dw, vcross(r, P));
+}
+
 /* ================================================================================== */
 /* brax/positional/pipeline.py: step                                                   */
 /* ================================================================================== */
@@ -300,45 +369,16 @@ static void positional_step(const Model* m, Link* s, const float* act) {
   /* ---- contact.get (sphere-plane, MJX plane_sphere) + collisions.resolve_position ---- */
   float dlam[MBD_MAXL][MBD_MAXCON];
   v3 cpos[MBD_MAXL][MBD_MAXCON];
-  const v3 nrm = V3(0.0f, 0.0f, 1.0f);
   for (int l = 0; l < L; ++l) {
     int ncon = LFi(m, MBD_F_NCON, l);
     if (ncon <= 0) continue;
     float im = LFf(m, MBD_F_INV_MASS, l);
     v3 dp = V3(0, 0, 0);
     q4 dq = Q4(0, 0, 0, 0);
-    for (int ci = 0; ci < ncon; ++ci) {
-      int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
-      float radius = LFf(m, base + 3, l), mu = LFf(m, base + 4, l);
-      v3 centre = vadd(s[l].p, vrotate(LF3(m, base, l), s[l].q));
-      float dist = centre.z - radius;
-      v3 cp = V3(centre.x, centre.y, centre.z - (radius + 0.5f * dist)); /* pos = c - n (r + dist/2) */
-      cpos[l][ci] = cp;
-      int coll = dist < 0.0f;
-      v3 r = vsub(cp, s[l].p);
-      v3 cr = vcross(r, nrm);
-      float w = im + vdot(cr, cr);
-      float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
-      v3 P = vscale(nrm, dl);
-      dp = vadd(dp, vscale(P, im));
-      dq = qadd(dq, qscale(vqmul(vcross(r, P), s[l].q), 0.5f));
-      /* static friction: cancel the tangential travel of the contact point since x_i_prev */
-      v3 rl = vinv_rotate(r, s[l].q);
-      v3 pbar = vadd(prev[l].p, vrotate(rl, prev[l].q));
-      v3 d = vsub(cp, pbar);
-      v3 dt_ = vsub(d, vscale(nrm, vdot(d, nrm)));
-      float ct;
-      v3 nt = vnormalize(dt_, &ct);
-      v3 crt = vcross(r, nt);
-      float wt = im + vdot(crt, crt);
-      float dlt = -ct / (wt + 1e-6f);
-      int stat = coll && (fabsf(dlt) < mu * fabsf(dl));
-      float dlt_m = stat ? dlt : 0.0f;
-      v3 Pt = vscale(nt, dlt_m);
-      dp = vadd(dp, vscale(Pt, im));
-      dq = qadd(dq, qscale(vqmul(vcross(r, Pt), s[l].q), 0.5f));
-      dlam[l][ci] = dl;
-    }
+    const v3 p0 = s[l].p;
+    const q4 q0 = s[l].q;
+    for (int ci = 0; ci < ncon; ++ci)
+      contact_position_plane(m, l, ci, im, p0, q0, prev[l].p, prev[l].q, &dp, &dq, &dlam[l][ci], &cpos[l][ci]);
     s[l].p = vfma(dp, m->collide_scale, s[l].p);
     s[l].q = qnormalize(qadd(s[l].q, qscale(dq, m->collide_scale)));
   }
@@ -355,37 +395,9 @@ static void positional_step(const Model* m, Link* s, const float* act) {
     if (ncon <= 0) continue;
     float im = LFf(m, MBD_F_INV_MASS, l);
     v3 dv = V3(0, 0, 0), dw = V3(0, 0, 0);
-    for (int ci = 0; ci < ncon; ++ci) {
-      int base = MBD_F_CON0 + ci * MBD_CON_STRIDE;
-      float mu = LFf(m, base + 4, l);
-      float dl = dlam[l][ci];
-      v3 r = vsub(cpos[l][ci], s[l].p);
-      v3 rel = vadd(s[l].v, vcross(s[l].w, r));
-      float vn = vdot(rel, nrm);
-      v3 vt = vsub(rel, vscale(nrm, vn));
-      float vtn;
-      v3 vtd = vnormalize(vt, &vtn);
-      float fr = mu * fabsf(dl) * m->inv_dt;
-      float mag = fr < vtn ? fr : vtn;
-      v3 dvel = vscale(vtd, -mag);
-      v3 crd = vcross(r, vtd);
-      float wd = im + vdot(crd, crd);
-      v3 p_dyn = vscale(dvel, 1.0f / (wd + 1e-6f));
-      v3 rel_old = vadd(before[l].v, vcross(before[l].w, r));
-      float vn_old = vdot(rel_old, nrm);
-      float rest = -m->elasticity * vn_old;
-      rest = rest < 0.0f ? rest : 0.0f;
-      v3 dv_rest = vscale(nrm, -vn + rest);
-      v3 crn = vcross(r, nrm);
-      float wn = im + vdot(crn, crn);
-      v3 p_rest = vscale(dv_rest, 1.0f / (wn + 1e-6f));
-      int sinking = vn_old <= 0.0f;
-      v3 P = p_dyn;
-      if (sinking) P = vadd(P, p_rest);
-      if (dl == 0.0f) P = V3(0, 0, 0);
-      dv = vadd(dv, vscale(P, im));
-      dw = vadd(dw, vcross(r, P));
-    }
+    const v3 v0 = s[l].v, w0 = s[l].w;
+    for (int ci = 0; ci < ncon; ++ci)
+      contact_velocity_plane(m, l, ci, im, s[l].p, v0, w0, before[l].v, before[l].w, cpos[l][ci], dlam[l][ci], &dv, &dw);
     s[l].v = vadd(s[l].v, dv);
     s[l].w = vadd(s[l].w, dw);
   }

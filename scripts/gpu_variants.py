@@ -10,10 +10,10 @@ st = torch.as_tensor(env.reset(rr).pipeline_state.raw, device="cuda:0")
 m = env.device_model()
 key = np.uint32([1, 2])
 res = {}
-for n in (8192, 1024, 65536):
+for n in (8192, 1024, 2048, 4096, 65536):
     H = 50
     Y0s = torch.empty((n, 850), device="cuda:0"); rews = torch.empty(n, device="cuda:0"); Yb = torch.zeros(850, device="cuda:0")
-    for v in (1, 2, 3, 4):
+    for v in (1, 2, 3, 5):
         ops.set_kernel_variant(v)
         for _ in range(2):
             ops.sample_rollout(m, st, key, n, 0, n, H, 0.88, Yb, Y0s, rews)
