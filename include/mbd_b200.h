@@ -85,6 +85,11 @@ int mbd_softmax_weights(const float* rews_all_dev, const float* logpd_all_dev, i
 int mbd_weighted_sum(const float* weights_dev, const float* Y0s_dev, int n_local, int HNu, float* scratch_dev,
                      float* partial_dev, mbd_stream s);
 
+/* einsum("n,nij->ij", weights, (Y0s - mu_0t)**2): the CMA-ES spread update of
+ * /root/reference/mbd/planners/path_integral.py:39-45, same deterministic order as mbd_weighted_sum. */
+int mbd_weighted_sqerr_sum(const float* weights_dev, const float* Y0s_dev, const float* mu_dev, int n_local, int HNu,
+                           float* scratch_dev, float* partial_dev, mbd_stream s);
+
 /* Ybar = tree-sum of the P rank partials; then score / Yim1 / Ybar_im1 literally as
  * mbd_planner.py:100,130-133.  coef = {sqrt(ab_i), 1/(1-ab_i), 1-ab_i, 1/sqrt(alpha_i), sqrt(ab_{i-1})}. */
 int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5],

@@ -21,7 +21,7 @@
 #define MBD_MAXL 16                /* max links (lanes per sample group) */
 #define MBD_MAXCHILD 4
 #define MBD_MAXDOF 3
-#define MBD_MAXCON 2               /* sphere-plane contacts per link */
+#define MBD_MAXCON 6               /* sphere-plane contacts per link (capsules contribute their two end caps) */
 #define MBD_MAXTRACK 8
 #define MBD_DOF_STRIDE 8
 #define MBD_CON_STRIDE 5
@@ -50,7 +50,7 @@ enum {
   MBD_HDR_WORDS = 64
 };
 
-enum { MBD_REWARD_HUMANOIDRUN = 0, MBD_REWARD_HUMANOIDTRACK = 1, MBD_REWARD_HOPPER = 2 };
+enum { MBD_REWARD_HUMANOIDRUN = 0, MBD_REWARD_HUMANOIDTRACK = 1, MBD_REWARD_HOPPER = 2, MBD_REWARD_HUMANOIDSTANDUP = 3 };
 
 /* ---- per-link fields ------------------------------------------------------------- */
 enum {

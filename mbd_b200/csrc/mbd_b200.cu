@@ -97,7 +97,7 @@ struct RolloutArgs {
   unsigned long long offs;
 };
 
-template <bool FUSED>
+template <bool FUSED, int CMAX>
 __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
   __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
   __shared__ __align__(8) uint64_t mbar;
@@ -176,19 +176,13 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
       v3 v0 = link_origin_vel(M, c, s);
       r_pre = 1.0f + ((-fabsf(v0.x - 1.6f) - fabsf(x0.z - 1.3f)) - fabsf(x0.y) * 0.1f);
     }
-    for (int f = 0; f < nsub; ++f) positional_step(M, c, K, s, tau);
+    for (int f = 0; f < nsub; ++f) positional_step<CMAX>(M, c, K, s, tau);
     if (c.l == 0) {
       float r;
       if (reward_kind == MBD_REWARD_HUMANOIDTRACK) {
         r = r_pre;
       } else {
-        v3 x0 = link_origin(M, c, s);
-        if (reward_kind == MBD_REWARD_HUMANOIDRUN) {
-          float dz = clampf(fabsf(x0.z - 1.3f), -1.0f, 1.0f);
-          r = (x0.x - dz) - fabsf(x0.y) * 0.1f;
-        } else {
-          r = x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;
-        }
+        r = reward_post(reward_kind, link_origin(M, c, s));
       }
       rsum += r;
       if (a.rewss && active) a.rewss[(size_t)n_local * a.H + t] = r;
@@ -231,7 +225,7 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
 }
 
 // ---- v2 rollout kernel: warp per link, lane per sample (xpbd_wpl.cuh) -------------------------------------
-template <bool FUSED, int NWARPS, int MINB, int SYNC, int SPLIT>
+template <bool FUSED, int NWARPS, int MINB, int SYNC, int SPLIT, int CMAX>
 __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a) {
   __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
   __shared__ __align__(8) uint64_t mbar;
@@ -323,19 +317,13 @@ __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a
       v3 v0 = link_origin_vel_w(M, 0, s);
       r_pre = 1.0f + ((-fabsf(v0.x - 1.6f) - fabsf(x0.z - 1.3f)) - fabsf(x0.y) * 0.1f);
     }
-    for (int f = 0; f < nsub; ++f) positional_step_wpl(M, c, S, Y, s, tau);
+    for (int f = 0; f < nsub; ++f) positional_step_wpl<CMAX>(M, c, S, Y, s, tau);
     if (l == 0) {
       float r;
       if (reward_kind == MBD_REWARD_HUMANOIDTRACK) {
         r = r_pre;
       } else {
-        v3 x0 = link_origin_w(M, 0, s);
-        if (reward_kind == MBD_REWARD_HUMANOIDRUN) {
-          float dz = clampf(fabsf(x0.z - 1.3f), -1.0f, 1.0f);
-          r = (x0.x - dz) - fabsf(x0.y) * 0.1f;
-        } else {
-          r = x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;
-        }
+        r = reward_post(reward_kind, link_origin_w(M, 0, s));
       }
       rsum += r;
       if (a.rewss && active) a.rewss[(size_t)n_local * a.H + t] = r;
@@ -519,13 +507,18 @@ __global__ void __launch_bounds__(kStatThreads) k_softmax_weights(const float* _
 
 // ---- weighted mean, deterministic order -----------------------------------------------------------------------
 // run r covers samples [r*kRun, (r+1)*kRun): out[r][j] = sum_n w[n]*Y[n][j] sequentially (fmaf)
-__global__ void k_wsum_runs(const float* __restrict__ w, const float* __restrict__ Y, int n_local, int HNu, float* __restrict__ runs) {
+// SQERR: accumulate w[n] * (Y[n][j] - mu[j])^2 instead (CMA-ES sigma update, path_integral.py:39-45)
+template <bool SQERR>
+__global__ void k_wsum_runs(const float* __restrict__ w, const float* __restrict__ Y, const float* __restrict__ mu, int n_local, int HNu,
+                            float* __restrict__ runs) {
   int j = blockIdx.y * blockDim.x + threadIdx.x;
   int r = blockIdx.x;
   if (j >= HNu) return;
   int n0 = r * kRun, n1 = min(n0 + kRun, n_local);
-  float acc = w[n0] * Y[(size_t)n0 * HNu + j];
-  for (int n = n0 + 1; n < n1; ++n) acc = fmaf(w[n], Y[(size_t)n * HNu + j], acc);
+  const float m = SQERR ? mu[j] : 0.0f;
+  auto term = [&](int n) { float y = Y[(size_t)n * HNu + j]; if (SQERR) { float d = y - m; return d * d; } return y; };
+  float acc = w[n0] * term(n0);
+  for (int n = n0 + 1; n < n1; ++n) acc = fmaf(w[n], term(n), acc);
   runs[(size_t)r * HNu + j] = acc;
 }
 // pairwise (adjacent) tree over `count` rows of [count][stride] -> value for column j; binary-counter
@@ -586,7 +579,7 @@ __global__ void k_update(const float* __restrict__ partials, int P, int HNu, con
 // =====================================================================================================
 struct mbd_model {
   uint32_t* blob_dev;
-  int L, nu, n_frames, ntrack;
+  int L, nu, n_frames, ntrack, max_ncon;
   // v2 kernel mappings (host side): one link per warp, and two same-type links per warp
   signed char wl1[MBD_MAXL][2], wl2[MBD_MAXL][2];
   unsigned long long offs1, offs2;
@@ -706,6 +699,9 @@ mbd_model* mbd_model_create(const uint32_t* blob_host, size_t nwords) {
   m->L = hi[MBD_H_NLINK]; m->nu = hi[MBD_H_NU]; m->n_frames = hi[MBD_H_NFRAMES]; m->ntrack = hi[MBD_H_NTRACK];
   if (m->L < 1 || m->L > MBD_MAXL || m->ntrack > MBD_MAXTRACK) { delete m; snprintf(g_err, sizeof(g_err), "bad link count"); return nullptr; }
   build_pairing(m, blob_host);
+  m->max_ncon = 0;
+  for (int l = 0; l < m->L; ++l) { int nc = hi[MBD_HDR_WORDS + MBD_F_NCON * MBD_MAXL + l]; if (nc > m->max_ncon) m->max_ncon = nc; }
+  if (m->max_ncon > MBD_MAXCON) { delete m; snprintf(g_err, sizeof(g_err), "too many contacts on one link"); return nullptr; }
   if (cudaMalloc(&m->blob_dev, nwords * 4) != cudaSuccess || cudaMemcpy(m->blob_dev, blob_host, nwords * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "mbd_model_create: cudaMalloc/cudaMemcpy failed");
     delete m;
@@ -731,12 +727,18 @@ int mbd_sample(const uint32_t key[2], int n_total, int n_begin, int n_local, int
   return MBD_OK;
 }
 
-#define MBD_LAUNCH_WPL(NW, MINB, SYNC, SPLIT, GRID, THREADS)                                             \
+#define MBD_LAUNCH_WPL_C(NW, MINB, SYNC, SPLIT, CMAX, GRID, THREADS)                                     \
   do {                                                                                                 \
     if (fused)                                                                                         \
-      mbd::k_rollout_wpl<true, NW, MINB, SYNC, SPLIT><<<GRID, THREADS, dyn, st>>>(a);                  \
+      mbd::k_rollout_wpl<true, NW, MINB, SYNC, SPLIT, CMAX><<<GRID, THREADS, dyn, st>>>(a);            \
     else                                                                                               \
-      mbd::k_rollout_wpl<false, NW, MINB, SYNC, SPLIT><<<GRID, THREADS, dyn, st>>>(a);                 \
+      mbd::k_rollout_wpl<false, NW, MINB, SYNC, SPLIT, CMAX><<<GRID, THREADS, dyn, st>>>(a);           \
+  } while (0)
+// contact arrays are sized by the model's worst link: 2 (humanoidrun/track) or MBD_MAXCON (humanoidstandup)
+#define MBD_LAUNCH_WPL(NW, MINB, SYNC, SPLIT, GRID, THREADS)                                           \
+  do {                                                                                                 \
+    if (m->max_ncon <= 2) MBD_LAUNCH_WPL_C(NW, MINB, SYNC, SPLIT, 2, GRID, THREADS);                   \
+    else MBD_LAUNCH_WPL_C(NW, MINB, SYNC, SPLIT, MBD_MAXCON, GRID, THREADS);                           \
   } while (0)
 
 static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cudaStream_t st) {
@@ -762,10 +764,13 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
     }
   } else {
     int grid = (a.n + mbd::kSPB - 1) / mbd::kSPB;
-    if (fused)
-      mbd::k_rollout<true><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
-    else
-      mbd::k_rollout<false><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+    if (m->max_ncon <= 2) {
+      if (fused) mbd::k_rollout<true, 2><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+      else mbd::k_rollout<false, 2><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+    } else {
+      if (fused) mbd::k_rollout<true, MBD_MAXCON><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+      else mbd::k_rollout<false, MBD_MAXCON><<<grid, mbd::kRolloutThreads, 0, st>>>(a);
+    }
   }
   CK(cudaGetLastError());
   return MBD_OK;
@@ -825,16 +830,30 @@ int mbd_softmax_weights(const float* rews_all_dev, const float* logpd_all_dev, i
   return MBD_OK;
 }
 
-int mbd_weighted_sum(const float* weights_dev, const float* Y0s_dev, int n_local, int HNu, float* scratch_dev, float* partial_dev,
-                     mbd_stream s) {
+static int weighted_sum_impl(const float* weights_dev, const float* Y0s_dev, const float* mu_dev, int n_local, int HNu, float* scratch_dev,
+                             float* partial_dev, mbd_stream s) {
   if (!weights_dev || !Y0s_dev || !scratch_dev || !partial_dev || n_local <= 0 || HNu <= 0) return MBD_EINVAL;
   int nruns = (n_local + mbd::kRun - 1) / mbd::kRun;
   dim3 grid(nruns, (HNu + 255) / 256);
-  mbd::k_wsum_runs<<<grid, 256, 0, (cudaStream_t)s>>>(weights_dev, Y0s_dev, n_local, HNu, scratch_dev);
+  if (mu_dev)
+    mbd::k_wsum_runs<true><<<grid, 256, 0, (cudaStream_t)s>>>(weights_dev, Y0s_dev, mu_dev, n_local, HNu, scratch_dev);
+  else
+    mbd::k_wsum_runs<false><<<grid, 256, 0, (cudaStream_t)s>>>(weights_dev, Y0s_dev, nullptr, n_local, HNu, scratch_dev);
   CK(cudaGetLastError());
   mbd::k_wsum_tree<<<(HNu + 127) / 128, 128, 0, (cudaStream_t)s>>>(scratch_dev, nruns, HNu, partial_dev);
   CK(cudaGetLastError());
   return MBD_OK;
+}
+
+int mbd_weighted_sum(const float* weights_dev, const float* Y0s_dev, int n_local, int HNu, float* scratch_dev, float* partial_dev,
+                     mbd_stream s) {
+  return weighted_sum_impl(weights_dev, Y0s_dev, nullptr, n_local, HNu, scratch_dev, partial_dev, s);
+}
+
+int mbd_weighted_sqerr_sum(const float* weights_dev, const float* Y0s_dev, const float* mu_dev, int n_local, int HNu, float* scratch_dev,
+                           float* partial_dev, mbd_stream s) {
+  if (!mu_dev) return MBD_EINVAL;
+  return weighted_sum_impl(weights_dev, Y0s_dev, mu_dev, n_local, HNu, scratch_dev, partial_dev, s);
 }
 
 int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5], float* Ybar_im1_dev,

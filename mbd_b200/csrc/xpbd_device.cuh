@@ -245,6 +245,7 @@ __device__ __forceinline__ void load_step_consts(const ModelSmem& M, StepConsts&
 
 // One brax.positional.pipeline.step for the link owned by this lane.  tau[k] = gear*clip(act) of
 // the lane's dof k (actuator.to_tau), already resolved by the caller.  All 32 lanes must call.
+template <int CMAX>
 __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCfg& c, const StepConsts& K,
                                                 LinkState& s, const float tau[MBD_MAXDOF]) {
   const bool jointed = c.ndof > 0;
@@ -354,17 +355,17 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     s.q = qnormalize(qadd(s.q, dq));
   }
   // ---- contact.get + collisions.resolve_position ---------------------------------------------------
-  float dlam[MBD_MAXCON];
-  v3 cpos[MBD_MAXCON];
+  float dlam[CMAX];
+  v3 cpos[CMAX];
 #pragma unroll
-  for (int ci = 0; ci < MBD_MAXCON; ++ci) { dlam[ci] = 0.0f; cpos[ci] = V3(0.0f, 0.0f, 0.0f); }
+  for (int ci = 0; ci < CMAX; ++ci) { dlam[ci] = 0.0f; cpos[ci] = V3(0.0f, 0.0f, 0.0f); }
   if (c.ncon > 0) {
     v3 dp = V3(0.0f, 0.0f, 0.0f);
     q4 dq = Q4(0.0f, 0.0f, 0.0f, 0.0f);
     const v3 p0 = s.p;
     const q4 q0 = s.q;
 #pragma unroll
-    for (int ci = 0; ci < MBD_MAXCON; ++ci)
+    for (int ci = 0; ci < CMAX; ++ci)
       if (ci < c.ncon) contact_position_plane(M, c.l, ci, c.inv_mass, p0, q0, prev.p, prev.q, dp, dq, dlam[ci], cpos[ci]);
     s.p = vfma(dp, K.collide_scale, s.p);
     s.q = qnormalize(qadd(s.q, qscale(dq, K.collide_scale)));
@@ -381,12 +382,23 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     v3 dv = V3(0.0f, 0.0f, 0.0f), dw = V3(0.0f, 0.0f, 0.0f);
     const v3 v0 = s.v, w0 = s.w;
 #pragma unroll
-    for (int ci = 0; ci < MBD_MAXCON; ++ci)
+    for (int ci = 0; ci < CMAX; ++ci)
       if (ci < c.ncon)
         contact_velocity_plane(M, c.l, ci, c.inv_mass, K.inv_dt, K.elasticity, s.p, v0, w0, v_before, w_before, cpos[ci], dlam[ci], dv, dw);
     s.v = vadd(s.v, dv);
     s.w = vadd(s.w, dw);
   }
+}
+
+// post-step rewards of the Brax-backed envs, from the root link's world position x.pos[0]
+__device__ __forceinline__ float reward_post(int kind, v3 x0) {
+  if (kind == MBD_REWARD_HUMANOIDRUN) {  // humanoidrun.py:46-51
+    float dz = clampf(fabsf(x0.z - 1.3f), -1.0f, 1.0f);
+    return (x0.x - dz) - fabsf(x0.y) * 0.1f;
+  }
+  if (kind == MBD_REWARD_HUMANOIDSTANDUP)  // humanoidstandup.py:50-56
+    return ((1.5f - clampf(fabsf(x0.z - 1.3f), -2.0f, 1.0f)) - fabsf(x0.x) * 0.1f) - fabsf(x0.y) * 0.1f;
+  return x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;  // hopper.py:57-65
 }
 
 // com.to_world pieces

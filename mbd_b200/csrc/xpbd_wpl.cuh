@@ -182,7 +182,7 @@ struct SyncNamed {
 
 // One brax.positional.pipeline.step for (link = this warp, sample = this lane).
 // All threads of the CTA must call.
-template <class Sync>
+template <int CMAX, class Sync>
 __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const WarpCfg& c, const WplSmem& S,
                                                     Sync& Y, LinkState& s, const float tau[MBD_MAXDOF]) {
   const bool jointed = c.ndof > 0;
@@ -313,15 +313,15 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     s.p = vadd(s.p, dp);
     s.q = qnormalize(qadd(s.q, dq));
   }
-  float dlam[MBD_MAXCON];
-  v3 cpos[MBD_MAXCON];
+  float dlam[CMAX];
+  v3 cpos[CMAX];
   if (c.ncon > 0) {
     v3 dp = V3(0.0f, 0.0f, 0.0f);
     q4 dq = Q4(0.0f, 0.0f, 0.0f, 0.0f);
     const v3 p0 = s.p;
     const q4 q0 = s.q;
 #pragma unroll
-    for (int ci = 0; ci < MBD_MAXCON; ++ci) {
+    for (int ci = 0; ci < CMAX; ++ci) {
       dlam[ci] = 0.0f; cpos[ci] = V3(0.0f, 0.0f, 0.0f);
       if (ci < c.ncon) contact_position_plane(M, c.l, ci, M.lf(MBD_F_INV_MASS, c.l), p0, q0, p_prev, q_prev, dp, dq, dlam[ci], cpos[ci]);
     }
@@ -338,7 +338,7 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     v3 dv = V3(0.0f, 0.0f, 0.0f), dw = V3(0.0f, 0.0f, 0.0f);
     const v3 v0 = s.v, w0 = s.w;
 #pragma unroll
-    for (int ci = 0; ci < MBD_MAXCON; ++ci)
+    for (int ci = 0; ci < CMAX; ++ci)
       if (ci < c.ncon)
         contact_velocity_plane(M, c.l, ci, M.lf(MBD_F_INV_MASS, c.l), M.hf(MBD_H_INV_DT), M.hf(MBD_H_ELASTICITY), s.p, v0, w0, v_before,
                                w_before, cpos[ci], dlam[ci], dv, dw);

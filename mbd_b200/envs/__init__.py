@@ -1,6 +1,7 @@
 """Env registry — mirrors /root/reference/mbd/envs/__init__.py:13-33 (same names, same ValueError)."""
 from .car2d import Car2d
 from .humanoidrun import HumanoidRun
+from .humanoidstandup import HumanoidStandup
 from .humanoidtrack import HumanoidTrack
 
 _NOT_VENDORED = {
@@ -9,7 +10,6 @@ _NOT_VENDORED = {
     "ant": "env and MJCF are Brax's stock `ant` (envs/__init__.py:30-31), not in the reference tree",
     "halfcheetah": "env and MJCF are Brax's stock `halfcheetah`, not in the reference tree",
     "pushT": "uses Brax's `generalized` backend (pushT.py:16), outside the positional hot path",
-    "humanoidstandup": "capsule-plane contacts on 9 links are not enabled in this round (SURVEY 8f.3)",
     "cartpole": "slide joints are not enabled in this round (SURVEY 8f.3)",
 }
 
@@ -17,6 +17,8 @@ _NOT_VENDORED = {
 def get_env(env_name: str):
     if env_name == "humanoidrun":
         return HumanoidRun()
+    elif env_name == "humanoidstandup":
+        return HumanoidStandup()
     elif env_name == "humanoidtrack":
         return HumanoidTrack()
     elif env_name == "car2d":

@@ -13,7 +13,7 @@ from .mjcf import System
 
 # ---- mirror of include/mbd_model.h (checked against the C side in tests/test_abi.py) ----
 MAGIC = 0x4D424431
-MAXL, MAXCHILD, MAXDOF, MAXCON, MAXTRACK = 16, 4, 3, 2, 8
+MAXL, MAXCHILD, MAXDOF, MAXCON, MAXTRACK = 16, 4, 3, 6, 8
 DOF_STRIDE, CON_STRIDE = 8, 5
 H_MAGIC, H_NLINK, H_NU, H_NFRAMES, H_REWARD, H_NTRACK, H_TRACK0 = 0, 1, 2, 3, 4, 5, 6
 H_DT = H_TRACK0 + MAXTRACK
@@ -37,7 +37,7 @@ D_STIFF, D_DAMP, D_LO, D_HI, D_ACT, D_GEAR, D_CLO, D_CHI = range(8)
 BLOB_WORDS = HDR_WORDS + NFIELDS * MAXL
 STATE_STRIDE = 13
 
-REWARD_HUMANOIDRUN, REWARD_HUMANOIDTRACK, REWARD_HOPPER = 0, 1, 2
+REWARD_HUMANOIDRUN, REWARD_HUMANOIDTRACK, REWARD_HOPPER, REWARD_HUMANOIDSTANDUP = 0, 1, 2, 3
 
 _BIG = 3.0e38  # stands in for +-inf limits (keeps the arithmetic NaN-free)
 

@@ -144,6 +144,12 @@ def weighted_sum(weights, Y0s, HNu, scratch, partial_out):
                                       _stream()), "mbd_weighted_sum")
 
 
+def weighted_sqerr_sum(weights, Y0s, mu, HNu, scratch, partial_out):
+    n_local = weights.numel()
+    check(_lib.lib().mbd_weighted_sqerr_sum(_p(_dev(weights)), _p(_dev(Y0s)), _p(_dev(mu)), n_local, HNu, _p(_dev(scratch)),
+                                            _p(_dev(partial_out)), _stream()), "mbd_weighted_sqerr_sum")
+
+
 def update(partials, P, HNu, Ybar_i, coef, out):
     c = (ctypes.c_float * 5)(*[float(v) for v in coef])
     check(_lib.lib().mbd_update(_p(_dev(partials)), P, HNu, _p(_dev(Ybar_i)), c, _p(_dev(out)), _stream()), "mbd_update")

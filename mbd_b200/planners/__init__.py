@@ -1,1 +1,1 @@
-from . import engine, mbd_planner  # noqa: F401
+from . import engine, mbd_planner, path_integral  # noqa: F401

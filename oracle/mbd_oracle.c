@@ -7,6 +7,7 @@
  *   - mbd.utils.rollout_us                             (/root/reference/mbd/utils.py:14-20)
  *   - HumanoidRun.step/_get_reward                     (/root/reference/mbd/envs/humanoidrun.py:34-51)
  *   - HumanoidTrack.step/_get_reward/eval_xref_logpd   (/root/reference/mbd/envs/humanoidtrack.py:63-106)
+ *   - HumanoidStandup.step/_get_reward                 (/root/reference/mbd/envs/humanoidstandup.py:40-56)
  *   - brax PipelineEnv.pipeline_step + brax.positional.pipeline.step (call site humanoidrun.py:36)
  *
  * PARITY UNPINNED for the Brax part: Brax is an un-vendored, un-pinned third-party
@@ -418,6 +419,10 @@ static float reward_post(const Model* m, const Link* s) {
     /* humanoidrun.py:46-51 */
     float dz = clampf(fabsf(x0.z - 1.3f), -1.0f, 1.0f);
     return (x0.x - dz) - fabsf(x0.y) * 0.1f;
+  }
+  if (m->reward == MBD_REWARD_HUMANOIDSTANDUP) {
+    /* humanoidstandup.py:50-56 */
+    return ((1.5f - clampf(fabsf(x0.z - 1.3f), -2.0f, 1.0f)) - fabsf(x0.x) * 0.1f) - fabsf(x0.y) * 0.1f;
   }
   if (m->reward == MBD_REWARD_HOPPER) {
     /* hopper.py:57-65 */

@@ -104,3 +104,26 @@ def run_diffusion(env: OracleEnv, seed, Nsample, H, Ndiffuse, temp, beta0=1e-4, 
     Yi = np.stack(Ybars)
     fin = env.rollout(Yi[-1][None], H, nthreads=1)
     return float(fin["rews"][0]), Yi, np.array(rews, dtype=f32)
+
+
+def update_once(env: OracleEnv, key, Nsample, H, sigma, mu_0t, temp, method, nthreads=0):
+    """path_integral.py:111-127 + the three update rules (:33-52).  Returns dict(mu, sigma, rew_mean, idx)."""
+    HNu = H * env.Nu
+    Y0s = orc.sample_Y0s(key, Nsample, HNu, sigma, mu_0t, nthreads=nthreads)
+    rews = env.rollout(Y0s, H, nthreads=nthreads)["rews"]
+    std = rews.std(dtype=f32)
+    std = f32(1.0) if std < 1e-4 else std   # shared guard (see mbd_b200/planners/path_integral.py docstring)
+    logp0 = ((rews - rews.mean(dtype=f32)) / std / f32(temp)).astype(f32)
+    w = softmax(logp0)
+    idx = None
+    if method == "cem":
+        idx = np.argsort(w, kind="stable")[::-1][:10]
+        mu = Y0s[idx].mean(axis=0, dtype=f32)
+    else:
+        mu = np.einsum("n,nj->j", w.astype(np.float64), Y0s.astype(np.float64)).astype(f32)
+        if method == "cma-es":
+            err = (Y0s - mu_0t[None]).astype(f32)
+            var = np.einsum("n,nj->j", w.astype(np.float64), (err * err).astype(np.float64)).astype(f32)
+            sigma = float(np.sqrt(var).mean(dtype=f32)) * sigma
+            sigma = max(sigma, 1e-3)
+    return dict(Y0s=Y0s, rews=rews, weights=w, mu=mu, sigma=sigma, rew_mean=rews.mean(dtype=f32), idx=idx)

@@ -43,6 +43,8 @@ def test_env_registry():
     t = mbd_b200.envs.get_env("humanoidtrack")
     assert (t.action_size, round(t.dt, 6), t.xref.shape, t.rew_xref) == (17, 0.03, (5, 50, 3), 1.0)
     assert t.track_body_idx.tolist() == [0, 5, 3, 6, 4] and t.ref_body_idx.tolist() == [11, 12, 13, 14, 15]
+    hs = mbd_b200.envs.get_env("humanoidstandup")
+    assert (hs.action_size, hs.observation_size, round(hs.dt, 6)) == (17, 47, 0.042)
     with pytest.raises(ValueError, match="Unknown environment"):
         mbd_b200.envs.get_env("nope")
     with pytest.raises(NotImplementedError):

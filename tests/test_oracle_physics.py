@@ -114,6 +114,30 @@ def test_actuator_torque_direction_and_limit(orc):
     assert kinematics.inverse(sys, x, r, a, v)[0][7] < np.pi / 2 + 0.15
 
 
+def test_capsule_rests_on_its_two_end_caps(orc):
+    """MJX plane_capsule = one sphere contact per end cap (humanoidstandup's torso/thigh/forearm geoms)."""
+    sys = _load(HDR.format(ang_damp=0, floor=FLOOR) +
+                '<body name="b" pos="0 0 0.3"><joint type="free" name="root"/>'
+                '<geom type="capsule" fromto="-0.2 0 0 0.2 0 0" size="0.05" contype="1" conaffinity="0"/></body></worldbody></mujoco>')
+    assert len(sys.contacts) == 2 and {round(float(c["pos"][0]), 3) for c in sys.contacts} == {-0.2, 0.2}
+    st, fin = _roll(orc, sys, 800)
+    assert abs(fin[0, 2] - 0.05) < 5e-3 and np.abs(fin[0, 10:13]).max() < 0.05
+    assert abs(fin[0, 3]) > 0.999          # stays flat: both caps carry it
+
+
+def test_humanoidstandup_oracle_is_stable(orc):
+    import mbd_b200
+    from mbd_b200 import prng
+    env = mbd_b200.envs.get_env("humanoidstandup")
+    assert len(env.sys.contacts) == 15
+    st = env.reset(prng.split(prng.PRNGKey(0))[1]).pipeline_state.raw
+    out = orc.xpbd_rollout(env.blob, st, np.zeros((1, 100, 17), np.float32), want_final=True, want_rewss=True)
+    fin = out["final"][0]
+    assert np.isfinite(fin).all() and 0.03 < fin[0, 2] < 0.2 and np.abs(fin[:, 10:13]).max() < 0.2   # lies on the floor
+    # reward = 1.5 - clip(|z-1.3|,-2,1) - 0.1|x| - 0.1|y| with the torso on the ground: ~0.5
+    assert abs(out["rewss"][0, -1] - 0.5) < 0.05
+
+
 def test_humanoid_regression_fixture(orc, humanoidrun_setup):
     """Oracle output pinned by a committed fixture (scripts/make_golden.py)."""
     env, b, st = humanoidrun_setup

@@ -174,3 +174,32 @@ def test_env_surface_step_equals_rollout(orc, humanoidrun_setup):
     assert s.pipeline_state.shape == (3,) and s.pipeline_state[0] < -0.5
     rr, xs = mbd_b200.utils.rollout_us(car.step, car.reset(None), np.float32([[0.3, 1.0]] * 3))
     assert len(xs) == 3 and np.allclose(xs[0], s.pipeline_state)
+
+
+@pytest.mark.parametrize("method", ["mppi", "cma-es", "cem"])
+def test_path_integral_update_once_vs_oracle(orc, humanoidrun_setup, method):
+    """MPPI / CMA-ES / CEM updates on the same kernels; CEM's top-10 index set is bit-exact."""
+    from mbd_b200.planners.path_integral import PathIntegralEngine
+    env, blob, st = humanoidrun_setup
+    Nn, H = 256, 50
+    key = np.uint32([21, 12])
+    mu0 = (np.random.default_rng(5).normal(size=850) * 0.2).astype(np.float32)
+    oenv = opl.OracleEnv("xpbd", 17, blob=blob, state=st)
+    ref = opl.update_once(oenv, key, Nn, H, 0.8, mu0, 0.1, method)
+    e = PathIntegralEngine(env, Nn, H, 0.1, st, method)
+    out = torch.empty(850, device=DEV)
+    mu, sigma, rew = e.update_once(key, torch.as_tensor(mu0, device=DEV), 0.8, out)
+    assert_bit_exact(N(e.rews_local), ref["rews"])
+    _close(N(mu), ref["mu"], f"{method} mean"); _close(rew.item(), ref["rew_mean"], "rews.mean()")
+    assert abs(sigma - ref["sigma"]) <= 1e-5 * max(1.0, ref["sigma"])
+    if method == "cem":
+        idx = torch.sort(e.weights, stable=True).indices.flip(0)[:10].cpu().numpy()
+        assert np.array_equal(idx, ref["idx"])
+
+
+def test_run_path_integral_cli_surface(capsys):
+    from mbd_b200.planners.path_integral import Args as PArgs, run_path_integral
+    rf, mus = run_path_integral(PArgs(env_name="car2d", Nsample=128, Nrefine=6, update_method="cma-es"), return_trajectory=True)
+    assert mus.shape == (5, 50, 2) and np.isfinite(rf) and "override temp_sample" in capsys.readouterr().out
+    with pytest.raises(KeyError):
+        run_path_integral(PArgs(env_name="car2d", Nsample=64, Nrefine=3, update_method="nope"))

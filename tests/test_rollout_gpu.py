@@ -120,6 +120,19 @@ def test_humanoidtrack_demo_bit_exact(orc, variant):
     assert np.all(ref["rewss"][:, 0] == ref["rewss"][0, 0])
 
 
+def test_humanoidstandup_bit_exact(orc, variant):
+    """contact-heavy env: 15 plane contacts, up to 5 on one link (capsule end caps + spheres)"""
+    env = mbd_b200.envs.get_env("humanoidstandup")
+    from mbd_b200 import prng
+    st = env.reset(prng.split(prng.PRNGKey(0))[1]).pipeline_state.raw
+    m = env.device_model(torch.device(DEV))
+    Y = _actions(np.random.default_rng(11), 45, 20, 17, 0.8)
+    ref = orc.xpbd_rollout(env.blob, st, Y, want_rewss=True, want_final=True)
+    out = ops.rollout(m, T(st), T(Y), want_rewss=True, want_final=True)
+    assert_bit_exact(N(out["final"]), ref["final"]); assert_bit_exact(N(out["rewss"]), ref["rewss"])
+    assert_bit_exact(N(out["rews"]), ref["rews"])
+
+
 def test_car2d_bit_exact(orc):
     car = mbd_b200.envs.get_env("car2d")
     params, xref = car.device_params()
