@@ -245,7 +245,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": f"{ENV_NAME} Nsample={n_total} Hsample={HSAMPLE} n_frames={NFRAMES} Ndiffuse={NDIFFUSE} "
                                    f"(steps i={NDIFFUSE - 1}..{NDIFFUSE - args.steps} of the real chain, seed 0)",
-                       "global_samples": n_total, "samples_per_gpu": e.n_local, "parallelism": f"sample-shard x{world}",
+                       "global_samples": n_total, "samples_per_gpu": e.n_local, "parallelism": f"sample-shard x{world}", "exchange": e.exchange,
                        "l2": "flushed between steps (256 MiB memset, untimed)",
                        "substeps_per_s": value * NFRAMES},
             "clocks": clocks,

@@ -90,6 +90,15 @@ int mbd_weighted_sum(const float* weights_dev, const float* Y0s_dev, int n_local
 int mbd_weighted_sqerr_sum(const float* weights_dev, const float* Y0s_dev, const float* mu_dev, int n_local, int HNu,
                            float* scratch_dev, float* partial_dev, mbd_stream s);
 
+/* Fused exchange over NVLink peer memory (replaces ncclAllGather for the two small per-step exchanges of
+ * reverse_once when the Nsample axis is sharded): an in-kernel cross-GPU barrier (system-scope flags in
+ * the peers' symmetric buffers) followed by direct peer loads.  peer_base_ptrs [P] are the base addresses
+ * of every rank's symmetric buffer (identical layout); dst_dev [P*count] receives rank-ordered data read
+ * from word offset src_off_words; flag rows live at flag_off_words (P words, zero-initialised, one row
+ * per call site); epoch must increase by one per call on the same row.  err_dev: set to 1 on timeout. */
+int mbd_peer_gather(const uint64_t* peer_base_ptrs, int P, int rank, size_t src_off_words, int count,
+                    size_t flag_off_words, uint32_t epoch, float* dst_dev, uint32_t* err_dev, mbd_stream s);
+
 /* Ybar = tree-sum of the P rank partials; then score / Yim1 / Ybar_im1 literally as
  * mbd_planner.py:100,130-133.  coef = {sqrt(ab_i), 1/(1-ab_i), 1-ab_i, 1/sqrt(alpha_i), sqrt(ab_{i-1})}. */
 int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5],

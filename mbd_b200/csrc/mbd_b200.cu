@@ -572,6 +572,53 @@ __global__ void k_update(const float* __restrict__ partials, int P, int HNu, con
   out[j] = Yim1 / c_sqrt_abm1;
 }
 
+
+// ---- fused cross-GPU exchange over NVLink peer memory ----------------------------------------------------
+// Replaces NCCL all_gather for the two tiny per-step exchanges (per-sample returns, rank partials):
+// every rank owns a symmetric buffer (torch symmetric memory: peer-mapped, same layout on all ranks).
+// One kernel = in-kernel barrier (system-scope release/acquire on per-peer flag words) + direct peer loads:
+//   1. CTA 0 publishes `epoch` into slot [rank] of every peer's flag row        (st.release.sys)
+//   2. every CTA waits until its own flag row shows `epoch` from all P peers     (ld.acquire.sys)
+//   3. dst[r][j] = peer_r[src_off + j] for all ranks r                           (ld.global.cv over NVLink)
+// Stream order guarantees the producer kernel of the data finished before step 1 runs on each rank.
+struct PeerArgs {
+  float* peer[8];
+  int P, rank, count;
+  unsigned long long src_off, flag_off;  // in 4-byte words from the buffer base
+  unsigned int epoch;
+  float* dst;        // [P*count] local
+  unsigned int* err; // local error word (set to 1 on a barrier timeout instead of hanging the GPU)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void k_peer_gather(PeerArgs a) {
+  if (blockIdx.x == 0 && threadIdx.x < a.P) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned int*>(a.peer[threadIdx.x]) + a.flag_off + a.rank, a.epoch);
+  }
+  if (threadIdx.x < a.P) {
+    const unsigned int* f = reinterpret_cast<const unsigned int*>(a.peer[a.rank]) + a.flag_off + threadIdx.x;
+    long long t0 = clock64();
+    while (ld_acquire_sys(f) < a.epoch) {
+      if (clock64() - t0 > 4000000000LL) { *a.err = 1u; break; }  // ~2 s: never hang the device
+    }
+  }
+  __syncthreads();
+  const int total = a.P * a.count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int r = i / a.count, j = i - r * a.count;
+    a.dst[i] = __ldcv(a.peer[r] + a.src_off + j);
+  }
+}
+
 }  // namespace mbd
 
 // =====================================================================================================
@@ -854,6 +901,22 @@ int mbd_weighted_sqerr_sum(const float* weights_dev, const float* Y0s_dev, const
                            float* partial_dev, mbd_stream s) {
   if (!mu_dev) return MBD_EINVAL;
   return weighted_sum_impl(weights_dev, Y0s_dev, mu_dev, n_local, HNu, scratch_dev, partial_dev, s);
+}
+
+int mbd_peer_gather(const uint64_t* peer_base_ptrs, int P, int rank, size_t src_off_words, int count, size_t flag_off_words,
+                    uint32_t epoch, float* dst_dev, uint32_t* err_dev, mbd_stream s) {
+  if (!peer_base_ptrs || P < 1 || P > 8 || rank < 0 || rank >= P || count <= 0 || !dst_dev || !err_dev || epoch == 0) return MBD_EINVAL;
+  mbd::PeerArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int r = 0; r < P; ++r) a.peer[r] = reinterpret_cast<float*>(peer_base_ptrs[r]);
+  a.P = P; a.rank = rank; a.count = count; a.src_off = src_off_words; a.flag_off = flag_off_words; a.epoch = epoch;
+  a.dst = dst_dev; a.err = err_dev;
+  int total = P * count;
+  int grid = (total + 1023) / 1024;
+  if (grid > 64) grid = 64;
+  mbd::k_peer_gather<<<grid, 256, 0, (cudaStream_t)s>>>(a);
+  CK(cudaGetLastError());
+  return MBD_OK;
 }
 
 int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5], float* Ybar_im1_dev,

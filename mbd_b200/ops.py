@@ -150,6 +150,12 @@ def weighted_sqerr_sum(weights, Y0s, mu, HNu, scratch, partial_out):
                                             _p(_dev(partial_out)), _stream()), "mbd_weighted_sqerr_sum")
 
 
+def peer_gather(peer_ptrs, P, rank, src_off_words, count, flag_off_words, epoch, dst, err):
+    arr = (ctypes.c_uint64 * P)(*[int(p) for p in peer_ptrs])
+    check(_lib.lib().mbd_peer_gather(arr, P, rank, src_off_words, count, flag_off_words, ctypes.c_uint32(epoch), _p(_dev(dst)),
+                                     ctypes.c_void_p(err.data_ptr()), _stream()), "mbd_peer_gather")
+
+
 def update(partials, P, HNu, Ybar_i, coef, out):
     c = (ctypes.c_float * 5)(*[float(v) for v in coef])
     check(_lib.lib().mbd_update(_p(_dev(partials)), P, HNu, _p(_dev(Ybar_i)), c, _p(_dev(out)), _stream()), "mbd_update")

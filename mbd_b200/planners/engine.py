@@ -4,15 +4,17 @@
 Per step and rank r of P (samples [r*N/P, (r+1)*N/P), noise addressed by GLOBAL index so the
 result does not depend on P):
   1. mbd_sample_rollout      fused sampling + rollouts   -> Y0s_local, rews_local (+logpd_local)
-  2. all_gather(rews[, logpd])                           (skipped for P == 1)
+  2. gather(rews[, logpd]) from all ranks                (skipped for P == 1; fused NVLink peer-memory
+                                                           kernel mbd_peer_gather, NCCL all_gather as fallback)
   3. mbd_softmax_weights     global mean/std/demo/softmax -> weights_local
   4. mbd_weighted_sum        partial Ybar over local samples (deterministic order)
-  5. all_gather(partial)                                 (skipped for P == 1)
+  5. gather(partial) from all ranks                      (same mechanism)
   6. mbd_update              tree-sum of rank partials + the literal update lines 130-133
 All launches go to the current CUDA stream; nothing synchronises with the host.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -53,9 +55,37 @@ class DiffusionEngine:
         d = self.device
         f = dict(device=d, dtype=torch.float32)
         self.Y0s = torch.empty((self.n_local, self.HNu), **f)
-        self.rews_local = torch.empty(self.n_local, **f)
+        # ---- exchange buffers.  P > 1 on CUDA: one peer-mapped symmetric buffer per rank
+        #      [rews n_local | logpd n_local | partial HNu | 2 flag rows of 8 words], exchanged by the fused
+        #      mbd_peer_gather kernel over NVLink; fallback (MBD_EXCHANGE=nccl, or no symmetric memory): NCCL.
+        self.sym = None
+        self.exchange = "none" if self.P == 1 else os.environ.get("MBD_EXCHANGE", "p2p")
+        if self.P > 1 and self.exchange == "p2p":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                import torch.distributed as dist
+                words = 2 * self.n_local + self.HNu + 16
+                self.sym = symm_mem.empty(words, dtype=torch.float32, device=d)
+                self.sym.zero_()
+                self.sym_hdl = symm_mem.rendezvous(self.sym, dist.group.WORLD if group is None else group)
+                self.peer_ptrs = [int(p) for p in self.sym_hdl.buffer_ptrs]
+                self.off_rews, self.off_logpd, self.off_partial = 0, self.n_local, 2 * self.n_local
+                self.off_flags = 2 * self.n_local + self.HNu
+                self.epoch = 0
+                self.xerr = torch.zeros(1, dtype=torch.int32, device=d)
+                torch.cuda.synchronize()
+                dist.barrier(group=group)
+            except Exception as e:  # noqa: BLE001
+                if os.environ.get("MBD_EXCHANGE") == "p2p":
+                    raise
+                self.sym, self.exchange = None, "nccl"
+        if self.sym is not None:
+            self.rews_local = self.sym[self.off_rews:self.off_rews + self.n_local]
+            self.logpd_local = self.sym[self.off_logpd:self.off_logpd + self.n_local] if self.enable_demo else None
+        else:
+            self.rews_local = torch.empty(self.n_local, **f)
+            self.logpd_local = torch.empty(self.n_local, **f) if self.enable_demo else None
         self.rews_all = self.rews_local if self.P == 1 else torch.empty(self.N, **f)
-        self.logpd_local = torch.empty(self.n_local, **f) if self.enable_demo else None
         self.logpd_all = None
         if self.enable_demo:
             self.logpd_all = self.logpd_local if self.P == 1 else torch.empty(self.N, **f)
@@ -63,7 +93,7 @@ class DiffusionEngine:
         self.scalars = torch.zeros(4, **f)
         self.logp_scratch = torch.empty(self.N, **f)
         self.run_scratch = torch.empty(((self.n_local + ops.RUN - 1) // ops.RUN) * self.HNu, **f)
-        self.partial = torch.empty(self.HNu, **f)
+        self.partial = self.sym[self.off_partial:self.off_partial + self.HNu] if self.sym is not None else torch.empty(self.HNu, **f)
         self.partials = self.partial if self.P == 1 else torch.empty((self.P, self.HNu), **f)
         self.Ybar_out = torch.empty(self.HNu, **f)
         self.launches_per_step = 5  # sample_rollout, softmax_weights, wsum_runs, wsum_tree, update
@@ -92,7 +122,18 @@ class DiffusionEngine:
                               logpd_out=self.logpd_local)
 
     def gather_phase(self):
-        if self.P > 1:
+        if self.sym is not None:
+            self.epoch += 1
+            if self.enable_demo:   # rews and logpd are adjacent: one gather of 2*n_local words per rank, then unzip
+                both = torch.empty((self.P, 2 * self.n_local), device=self.device)
+                ops.peer_gather(self.peer_ptrs, self.P, self.rank, self.off_rews, 2 * self.n_local, self.off_flags, self.epoch, both,
+                                self.xerr)
+                self.rews_all.view(self.P, self.n_local).copy_(both[:, : self.n_local])
+                self.logpd_all.view(self.P, self.n_local).copy_(both[:, self.n_local:])
+            else:
+                ops.peer_gather(self.peer_ptrs, self.P, self.rank, self.off_rews, self.n_local, self.off_flags, self.epoch,
+                                self.rews_all, self.xerr)
+        elif self.P > 1:
             self.plan.all_gather(self.rews_all, self.rews_local)
             if self.enable_demo:
                 self.plan.all_gather(self.logpd_all, self.logpd_local)
@@ -102,7 +143,10 @@ class DiffusionEngine:
         ops.softmax_weights(self.rews_all, self.logpd_all, self.n_begin, self.n_local, self.temp, self.rew_xref, self.weights,
                             self.scalars, self.logp_scratch)
         ops.weighted_sum(self.weights, self.Y0s, self.HNu, self.run_scratch, self.partial)
-        if self.P > 1:
+        if self.sym is not None:
+            ops.peer_gather(self.peer_ptrs, self.P, self.rank, self.off_partial, self.HNu, self.off_flags + 8, self.epoch,
+                            self.partials, self.xerr)
+        elif self.P > 1:
             self.plan.all_gather(self.partials, self.partial)
         ops.update(self.partials, self.P, self.HNu, Ybar_i, coef, out)
         return out

@@ -34,6 +34,9 @@ for i in (99, 98, 97):
     key2 = prng.split(key)[1]; key = prng.split(key)[0]
     out, rew = e.reverse_once(key2, float(sigmas[i]), Yb, eng.update_coef(alphas, alphas_bar, i))
     Yb = out.clone(); outs.append(out.cpu().numpy().copy()); outs.append(np.float32([rew.item()]))
+assert e.P == 1 or e.exchange == os.environ.get("MBD_EXCHANGE", "p2p"), e.exchange
+if e.sym is not None:
+    assert int(e.xerr.item()) == 0
 if e.rank == 0:
     np.save(os.environ["MBD_OUT"], np.concatenate(outs))
 if e.P > 1:
@@ -52,8 +55,10 @@ def test_two_rank_nccl_equals_single_gpu(tmp_path):
     env = dict(os.environ, MBD_ROOT=ROOT)
     env1 = dict(env, MBD_OUT=str(tmp_path / "p1.npy"))
     subprocess.run([sys.executable, str(w)], check=True, env=env1, timeout=600)
-    env2 = dict(env, MBD_OUT=str(tmp_path / "p2.npy"))
-    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                    "--master-port", str(_port()), str(w)], check=True, env=env2, timeout=600)
-    a, b = np.load(tmp_path / "p1.npy"), np.load(tmp_path / "p2.npy")
-    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    a = np.load(tmp_path / "p1.npy")
+    for mode in ("p2p", "nccl"):   # fused NVLink peer-memory gather, and the NCCL all_gather fallback
+        env2 = dict(env, MBD_OUT=str(tmp_path / f"p2_{mode}.npy"), MBD_EXCHANGE=mode)
+        subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(_port()), str(w)], check=True, env=env2, timeout=600)
+        b = np.load(tmp_path / f"p2_{mode}.npy")
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), mode
