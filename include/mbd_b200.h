@@ -99,6 +99,10 @@ int mbd_weighted_sqerr_sum(const float* weights_dev, const float* Y0s_dev, const
 int mbd_peer_gather(const uint64_t* peer_base_ptrs, int P, int rank, size_t src_off_words, int count,
                     size_t flag_off_words, uint32_t epoch, float* dst_dev, uint32_t* err_dev, mbd_stream s);
 
+/* Test hook: element-wise MBD_DIV (op 0), MBD_RCP (1), MBD_SQRT (2), mbd_atan2f (3) — the branch-free
+ * exact device sequences of include/mbd_fp32.h — so tests can compare them with IEEE results bit for bit. */
+int mbd_test_arith(int op, const float* a_dev, const float* b_dev, float* out_dev, int n, mbd_stream s);
+
 /* Ybar = tree-sum of the P rank partials; then score / Yim1 / Ybar_im1 literally as
  * mbd_planner.py:100,130-133.  coef = {sqrt(ab_i), 1/(1-ab_i), 1-ab_i, 1/sqrt(alpha_i), sqrt(ab_{i-1})}. */
 int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5],

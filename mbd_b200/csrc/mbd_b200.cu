@@ -437,6 +437,16 @@ __global__ void k_car2d(CarArgs a) {
   if (a.logpd && a.xref) a.logpd[i] = 0.0f - acc / (float)a.H;
 }
 
+// ---- test hook: the exact div / rcp / sqrt device sequences on arrays (tests/test_rollout_gpu.py) ----------
+__global__ void k_test_arith(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (op == 0) o[i] = MBD_DIV(a[i], b[i]);
+  else if (op == 1) o[i] = MBD_RCP(a[i]);
+  else if (op == 2) o[i] = MBD_SQRT(a[i]);
+  else o[i] = mbd_atan2f(a[i], b[i]);
+}
+
 // ---- reward statistics + softmax (mbd_planner.py:110-127), single CTA ------------------------------------
 constexpr int kStatThreads = 1024;
 enum { OP_SUM = 0, OP_MAX = 1 };
@@ -792,7 +802,9 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   const int L = m->L;
   int variant = g_kernel_variant;
   // auto: small shards keep more warps in flight with the lane-per-link kernel; large ones use v2
-  if (variant == 0) variant = (L == 11) ? (a.n >= 2048 ? 3 : 1) : 2;
+  // (measured, humanoidrun): < 2048 samples v1 keeps more warps in flight; one CTA per SM favours the
+  // named edge barriers; two CTAs per SM (> 148 CTAs) favour plain CTA barriers (better I-cache locality)
+  if (variant == 0) variant = (L == 11) ? (a.n < 2048 ? 1 : (a.n <= 148 * 32 ? 3 : 2)) : 2;
   if (variant >= 2) {
     size_t dyn = (size_t)L * (mbd::kXF + mbd::kEF) * mbd::kWplLanes * sizeof(float);
     const bool split = (variant == 5);
@@ -915,6 +927,13 @@ int mbd_peer_gather(const uint64_t* peer_base_ptrs, int P, int rank, size_t src_
   int grid = (total + 1023) / 1024;
   if (grid > 64) grid = 64;
   mbd::k_peer_gather<<<grid, 256, 0, (cudaStream_t)s>>>(a);
+  CK(cudaGetLastError());
+  return MBD_OK;
+}
+
+int mbd_test_arith(int op, const float* a_dev, const float* b_dev, float* out_dev, int n, mbd_stream s) {
+  if (!a_dev || !b_dev || !out_dev || n <= 0 || op < 0 || op > 3) return MBD_EINVAL;
+  mbd::k_test_arith<<<(n + 255) / 256, 256, 0, (cudaStream_t)s>>>(op, a_dev, b_dev, out_dev, n);
   CK(cudaGetLastError());
   return MBD_OK;
 }

@@ -39,8 +39,8 @@ __device__ __forceinline__ v3 vcross(v3 a, v3 b) {
   return V3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
 __device__ __forceinline__ v3 vnormalize(v3 a, float* norm) {
-  float n = sqrtf(vdot(a, a));
-  float inv = (n == 0.0f) ? 0.0f : 1.0f / n;
+  float n = MBD_SQRT(vdot(a, a));
+  float inv = (n == 0.0f) ? 0.0f : MBD_RCP(n);
   *norm = n;
   return vscale(a, inv);
 }
@@ -66,8 +66,8 @@ __device__ __forceinline__ v3 vrotate(v3 v, q4 q) {
 }
 __device__ __forceinline__ v3 vinv_rotate(v3 v, q4 q) { return vrotate(v, qconj(q)); }
 __device__ __forceinline__ q4 qnormalize(q4 q) {
-  float n = sqrtf(fmaf(q.z, q.z, fmaf(q.y, q.y, fmaf(q.x, q.x, q.w * q.w))));
-  float inv = 1.0f / n;
+  float n = MBD_SQRT(fmaf(q.z, q.z, fmaf(q.y, q.y, fmaf(q.x, q.x, q.w * q.w))));
+  float inv = MBD_RCP(n);
   return Q4(q.w * inv, q.x * inv, q.y * inv, q.z * inv);
 }
 __device__ __forceinline__ q4 qadd(q4 a, q4 b) { return Q4(a.w + b.w, a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -117,19 +117,19 @@ __device__ __forceinline__ void contact_position_plane(const ModelSmem& M, int l
   bool coll = dist < 0.0f;
   v3 r = vsub(cp, p);
   float w = im + fmaf(r.x, r.x, r.y * r.y);
-  float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
+  float dl = coll ? MBD_DIV(-dist, w + 1e-6f) : 0.0f;
   dp.z = dp.z + dl * im;
   dq = qadd(dq, qscale(vqmul_xy(r.y * dl, -(r.x * dl), q), 0.5f));
   // static friction: cancel the tangential travel of the contact point since x_i_prev
   v3 rl = vinv_rotate(r, q);
   v3 pbar = vadd(p_prev, vrotate(rl, q_prev));
   float dx = cp.x - pbar.x, dy = cp.y - pbar.y;
-  float ct = sqrtf(fmaf(dy, dy, dx * dx));
-  float inv = (ct == 0.0f) ? 0.0f : 1.0f / ct;
+  float ct = MBD_SQRT(fmaf(dy, dy, dx * dx));
+  float inv = (ct == 0.0f) ? 0.0f : MBD_RCP(ct);
   float ntx = dx * inv, nty = dy * inv;
   float c1 = -(r.z * nty), c2 = r.z * ntx, c3 = fmaf(r.x, nty, -(r.y * ntx));
   float wt = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
-  float dlt = -ct / (wt + 1e-6f);
+  float dlt = MBD_DIV(-ct, wt + 1e-6f);
   bool stat = coll && (fabsf(dlt) < mu * fabsf(dl));
   float m = stat ? dlt : 0.0f;
   float ptx = ntx * m, pty = nty * m;
@@ -146,21 +146,21 @@ __device__ __forceinline__ void contact_velocity_plane(const ModelSmem& M, int l
   v3 r = vsub(cp, p);
   v3 rel = vadd(v, vcross(w, r));
   float vn = rel.z;
-  float vtn = sqrtf(fmaf(rel.y, rel.y, rel.x * rel.x));
-  float inv = (vtn == 0.0f) ? 0.0f : 1.0f / vtn;
+  float vtn = MBD_SQRT(fmaf(rel.y, rel.y, rel.x * rel.x));
+  float inv = (vtn == 0.0f) ? 0.0f : MBD_RCP(vtn);
   float tdx = rel.x * inv, tdy = rel.y * inv;
   float fr = mu * fabsf(dl) * inv_dt;
   float mag = fr < vtn ? fr : vtn;
   float c1 = -(r.z * tdy), c2 = r.z * tdx, c3 = fmaf(r.x, tdy, -(r.y * tdx));
   float wd = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
-  float kd = 1.0f / (wd + 1e-6f);
+  float kd = MBD_RCP(wd + 1e-6f);
   float pdx = (tdx * -mag) * kd, pdy = (tdy * -mag) * kd;
   v3 rel_old = vadd(v_before, vcross(w_before, r));
   float vn_old = rel_old.z;
   float rest = -elasticity * vn_old;
   rest = rest < 0.0f ? rest : 0.0f;
   float wn = im + fmaf(r.x, r.x, r.y * r.y);
-  float prz = (-vn + rest) * (1.0f / (wn + 1e-6f));
+  float prz = (-vn + rest) * (MBD_RCP(wn + 1e-6f));
   v3 P = V3(pdx, pdy, (vn_old <= 0.0f) ? prz : 0.0f);
   if (dl == 0.0f) P = V3(0.0f, 0.0f, 0.0f);
   dv = vadd(dv, vscale(P, im));
@@ -181,7 +181,7 @@ __device__ __forceinline__ void axis_angle_ang(q4 j, float parity, JointAngles& 
   o.r10 = 2.0f * fmaf(x, y, w * z);
   o.r20 = 2.0f * fmaf(x, z, -(w * y));
   float psi = mbd_atan2f(-r12, r22);
-  float cth = sqrtf(fmaf(r01, r01, r00 * r00));
+  float cth = MBD_SQRT(fmaf(r01, r01, r00 * r00));
   float theta = mbd_atan2f(r02, cth);
   float phi = mbd_atan2f(-r01, r00);
   float ln;
@@ -308,7 +308,7 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     v3 crc = vcross(rcw, n), crp = vcross(rpw, n);
     float w_c = im_c + vdot(crc, crc);
     float w_p = fmaf(ii_p, vdot(crp, crp), im_p);
-    float dl = -cn / (w_p + w_c + 1e-6f);
+    float dl = MBD_DIV(-cn, w_p + w_c + 1e-6f);
     v3 P = vscale(n, dl);
     v3 dp_c = vscale(P, im_c);
     q4 dq_c = qscale(vqmul(vcross(rcw, P), s.q), 0.5f);
@@ -332,7 +332,7 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     float th;
     v3 na = vnormalize(dq, &th);
     float nn = vdot(na, na);
-    float dla = -th / (fmaf(ii_p, nn, nn) + 1e-6f);
+    float dla = MBD_DIV(-th, fmaf(ii_p, nn, nn) + 1e-6f);
     v3 Pa = vscale(na, dla);
     q4 dqa_c = qscale(vqmul(Pa, s.q), 0.5f);
     q4 dqa_p = qscale(vqmul(Pa, qp), -0.5f * ii_p);

@@ -260,7 +260,7 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     v3 crc = vcross(rcw, n), crp = vcross(rpw, n);
     float w_c = im_c + vdot(crc, crc);
     float w_p = fmaf(ii_p, vdot(crp, crp), im_p);
-    float dl = -cn / (w_p + w_c + 1e-6f);
+    float dl = MBD_DIV(-cn, w_p + w_c + 1e-6f);
     v3 P = vscale(n, dl);
     v3 dp_c = vscale(P, im_c);
     q4 dq_c = qscale(vqmul(vcross(rcw, P), s.q), 0.5f);
@@ -290,7 +290,7 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     float th;
     v3 na = vnormalize(dq, &th);
     float nn = vdot(na, na);
-    float dla = -th / (fmaf(ii_p, nn, nn) + 1e-6f);
+    float dla = MBD_DIV(-th, fmaf(ii_p, nn, nn) + 1e-6f);
     v3 Pa = vscale(na, dla);
     q4 dqa_c = qscale(vqmul(Pa, s.q), 0.5f);
     q4 dqa_p = qscale(vqmul(Pa, qp), -0.5f * ii_p);

@@ -78,6 +78,36 @@ def test_humanoidrun_golden_fixture(hr, variant):
     assert_bit_exact(N(Y).reshape(32, 50, 17), g["Y0s"], "sampled Y0s")
 
 
+def test_exact_arith(orc):
+    """The branch-free device div / rcp / sqrt (hardware fast path written out, include/mbd_fp32.h) are
+    correctly rounded on the operand ranges of the path: bit-equal to IEEE (numpy float32) results."""
+    import ctypes
+    from mbd_b200 import _lib
+    rng = np.random.default_rng(0)
+    n = 1 << 22
+
+    def run(op, a, b):
+        ta, tb = T(a), T(b)
+        out = torch.empty(n, device=DEV)
+        _lib.check(_lib.lib().mbd_test_arith(op, ctypes.c_void_p(ta.data_ptr()), ctypes.c_void_p(tb.data_ptr()),
+                                             ctypes.c_void_p(out.data_ptr()), n, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "mbd_test_arith")
+        return N(out)
+
+    mag = lambda lo, hi: (np.float32(10.0) ** rng.uniform(lo, hi, n).astype(np.float32)) * rng.choice(np.float32([-1, 1]), n)
+    a, b = mag(-12, 6), np.abs(mag(-9, 9))
+    a[:4096] = 0.0; a[4096:8192] = -0.0                      # zero dividends (normalised zero vectors)
+    assert_bit_exact(run(0, a, b), a / b, "div")
+    assert_bit_exact(run(0, a, -b), a / -b, "div, negative divisor")
+    x = np.abs(mag(-12, 12))
+    assert_bit_exact(run(1, x, x), np.float32(1.0) / x, "rcp")
+    x = np.abs(mag(-28, 20)); x[:4096] = 0.0
+    assert_bit_exact(run(2, x, x), np.sqrt(x), "sqrt")
+    y, xx = mag(-6, 3), mag(-6, 3)
+    y[:1000] = 0.0; xx[500:1500] = 0.0
+    assert_bit_exact(run(3, y, xx), orc.fmap("atan2", y, xx), "atan2 (device division inside)")
+
+
 def test_sampling_bit_exact(orc):
     key = np.uint32([0xDEADBEEF, 42])
     rng = np.random.default_rng(0)
