@@ -300,7 +300,6 @@ __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a
     if (M.hi(MBD_H_TRACK0 + k) == l) my_track = k;
   __syncthreads();
   if constexpr (SYNC != 0) Y.arrive_pose(l);  // the initial pose is published
-
   float rsum = 0.0f, tacc = 0.0f;
   const float* urow = a.Y0s + (size_t)n_rd * HNu;
   for (int t = 0; t < a.H; ++t) {
