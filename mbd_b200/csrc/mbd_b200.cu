@@ -816,6 +816,7 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
     } else {
       int grid = (a.n + mbd::kWplLanes - 1) / mbd::kWplLanes;
       if (L == 11 && variant == 2) MBD_LAUNCH_WPL(11, 2, 0, 1, grid, 32 * L);       // CTA-wide barriers
+      else if (L == 11 && variant == 3 && grid <= 148) MBD_LAUNCH_WPL(11, 1, 2, 1, grid, 32 * L);  // one CTA per SM: no register cap
       else if (L == 11 && variant == 3) MBD_LAUNCH_WPL(11, 2, 2, 1, grid, 32 * L);  // named edge barriers
       else if (L == 11 && variant == 4) MBD_LAUNCH_WPL(11, 2, 1, 1, grid, 32 * L);  // mbarrier point-to-point
       else MBD_LAUNCH_WPL(MBD_MAXL, 1, 0, 1, grid, 32 * L);
