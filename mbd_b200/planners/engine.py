@@ -125,7 +125,9 @@ class DiffusionEngine:
         if self.sym is not None:
             self.epoch += 1
             if self.enable_demo:   # rews and logpd are adjacent: one gather of 2*n_local words per rank, then unzip
-                both = torch.empty((self.P, 2 * self.n_local), device=self.device)
+                if not hasattr(self, "_both"):
+                    self._both = torch.empty((self.P, 2 * self.n_local), device=self.device)
+                both = self._both
                 ops.peer_gather(self.peer_ptrs, self.P, self.rank, self.off_rews, 2 * self.n_local, self.off_flags, self.epoch, both,
                                 self.xerr)
                 self.rews_all.view(self.P, self.n_local).copy_(both[:, : self.n_local])
@@ -150,6 +152,12 @@ class DiffusionEngine:
             self.plan.all_gather(self.partials, self.partial)
         ops.update(self.partials, self.P, self.HNu, Ybar_i, coef, out)
         return out
+
+    def check_exchange(self):
+        """Raises if a fused peer gather ever timed out on its cross-GPU barrier (a peer died or diverged).
+        Synchronises: call it outside the step loop."""
+        if self.sym is not None and int(self.xerr.item()) != 0:
+            raise ops.MbdError("mbd_peer_gather: cross-GPU barrier timed out (a peer rank stopped participating)")
 
     def reverse_once(self, key, sigma: float, Ybar_i: torch.Tensor, coef, out: Optional[torch.Tensor] = None):
         """One diffusion step.  Returns (Ybar_im1 [HNu] device tensor, rews.mean() device scalar view)."""

@@ -104,6 +104,7 @@ def run_diffusion(args: Args, log_every: int = 10, return_trajectory: bool = Fal
             # the reference formats rew every step (a device->host sync each step, mbd_planner.py:147);
             # here the sync is paid every `log_every` steps only
             pbar.set_postfix({"rew": f"{rews[i].item():.2e}"})
+    engine.check_exchange()
     Yi = Ybars[: args.Ndiffuse - 1].flip(0).reshape(args.Ndiffuse - 1, args.Hsample, Nu)  # jnp.array(Ybars) order
 
     if not args.not_render and _is_main():
