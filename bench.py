@@ -196,10 +196,14 @@ def run_gpu(args):
             e0.record()
             if host_io:  # the reference-facing call with HOST buffers: H2D of the iterate, D2H of result + reward
                 Ybar.copy_(h_in, non_blocking=True)
-            e.rollout_phase(k, float(sigmas[i]), Ybar)
-            e2.record()
-            e.gather_phase()
-            e.reduce_phase(Ybar, coef, out)
+            if e.single_kernel:      # one cooperative kernel does the whole step
+                e.reverse_once(k, float(sigmas[i]), Ybar, coef, out=out)
+                e2.record()
+            else:
+                e.rollout_phase(k, float(sigmas[i]), Ybar)
+                e2.record()
+                e.gather_phase()
+                e.reduce_phase(Ybar, coef, out)
             if host_io:
                 h_out[:HNu].copy_(out, non_blocking=True)
                 h_out[HNu:].copy_(e.scalars[:1], non_blocking=True)
@@ -250,8 +254,9 @@ def run_gpu(args):
                        "substeps_per_s": value * NFRAMES},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": HNu * 4 + 8, "d2h_bytes_per_step": HNu * 4 + 4},
-            "gpu_launches": e.launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_rollout<true> (fused sampling + rollouts)", "achieved": achieved,
+            "gpu_launches": e.launches_last_step * args.steps,
+            "roofline": {"bound": "hbm", "kernel": ("k_reverse_step_wpl (sampling + rollouts + statistics + weighted mean + update, one launch)"
+                                                   if e.single_kernel else "k_rollout_wpl<true> (fused sampling + rollouts)"), "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_s * 1e3,
                          "note": "path is fp32-issue bound, not HBM bound (SURVEY F7): see DESIGN.md roofline section"},

@@ -21,6 +21,7 @@ extern "C" {
 #define MBD_EINVAL (-1)  /* bad argument / bad blob */
 #define MBD_ECUDA (-2)   /* CUDA runtime error (see mbd_last_error) */
 #define MBD_ENOGPU (-3)  /* no CUDA device: there is deliberately NO CPU fallback */
+#define MBD_EUNSUPPORTED (-4) /* this fused entry point does not cover the configuration: use the separate calls */
 
 typedef struct mbd_model mbd_model;
 typedef void* mbd_stream; /* cudaStream_t */
@@ -61,6 +62,16 @@ int mbd_rollout(const mbd_model* m, const float* state_init_dev, const float* Y0
 int mbd_sample_rollout(const mbd_model* m, const float* state_init_dev, const uint32_t key[2], int n_total,
                        int n_begin, int n_local, int H, float sigma, const float* Ybar_dev, float* Y0s_dev,
                        float* rews_dev, const float* xref_dev, int href, float* logpd_dev, mbd_stream s);
+
+/* The whole of reverse_once (mbd_planner.py:97-135, enable_demo False, one GPU) as ONE cooperative kernel:
+ * sampling + rollouts, grid barrier, reward statistics + softmax (recomputed per CTA), weighted-mean runs, grid
+ * barrier, pairwise tree + update.  Bit-identical to mbd_sample_rollout + mbd_softmax_weights + mbd_weighted_sum
+ * + mbd_update.  Returns MBD_EUNSUPPORTED when the configuration is not covered (model shape, shard too large
+ * for co-residency or too small to benefit): the caller then uses the separate entry points.
+ * runs_dev: ceil(n/64)*H*Nu floats; scalars_dev[4] as in mbd_softmax_weights. */
+int mbd_reverse_step(const mbd_model* m, const float* state_init_dev, const uint32_t key[2], int n, int H, float sigma,
+                     const float* Ybar_i_dev, float temp, const float coef[5], float* Y0s_dev, float* rews_dev,
+                     float* weights_dev, float* scalars_dev, float* runs_dev, float* Ybar_im1_dev, mbd_stream s);
 
 /* Car2d (self-contained env, /root/reference/mbd/envs/car2d.py:77-102).
  * params_dev: [obs_center(11x2), obs_radius, dt, dt/2, dt/6]; x0_dev [3]; xref_dev [href,2] or NULL.

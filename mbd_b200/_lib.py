@@ -46,6 +46,8 @@ def lib():
                               ctypes.c_int, c_vp]
     L.mbd_sample_rollout.argtypes = [c_vp, c_vp, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                      c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp]
+    L.mbd_reverse_step.argtypes = [c_vp, c_vp, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.c_float, c_vp, ctypes.c_float, c_f32p,
+                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     L.mbd_car2d_rollout.argtypes = [c_vp, c_vp, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                     c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]
     L.mbd_softmax_weights.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
@@ -61,7 +63,7 @@ def lib():
 
 
 EXPORTS = ["mbd_set_kernel_variant", "mbd_layout_info", "mbd_last_error", "mbd_device_count", "mbd_model_create", "mbd_model_destroy", "mbd_sample",
-           "mbd_rollout", "mbd_sample_rollout", "mbd_car2d_rollout", "mbd_softmax_weights", "mbd_weighted_sum", "mbd_weighted_sqerr_sum", "mbd_peer_gather", "mbd_test_arith", "mbd_update"]
+           "mbd_rollout", "mbd_sample_rollout", "mbd_reverse_step", "mbd_car2d_rollout", "mbd_softmax_weights", "mbd_weighted_sum", "mbd_weighted_sqerr_sum", "mbd_peer_gather", "mbd_test_arith", "mbd_update"]
 
 
 def check(rc: int, what: str):

@@ -15,6 +15,8 @@
 
 #include <type_traits>
 
+#include <cooperative_groups.h>
+
 #include "mbd_b200.h"
 #include "mbd_fp32.h"
 #include "mbd_model.h"
@@ -225,13 +227,9 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
 }
 
 // ---- v2 rollout kernel: warp per link, lane per sample (xpbd_wpl.cuh) -------------------------------------
-template <bool FUSED, int NWARPS, int MINB, int SYNC, int SPLIT, int CMAX>
-__global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a) {
-  __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
-  __shared__ __align__(8) uint64_t mbar;
-  __shared__ __align__(8) uint64_t edge_bars[2 * MBD_MAXL];
-  extern __shared__ __align__(16) float dyn[];
-  stage_model_tma(sblob, &mbar, a.blob);
+template <bool FUSED, int SYNC, int SPLIT, int CMAX>
+__device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sblob, uint64_t* mbar_p, uint64_t* edge_bars, float* dyn) {
+  stage_model_tma(sblob, mbar_p, a.blob);
   ModelSmem M;
   M.f = sblob;
 
@@ -363,6 +361,15 @@ __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a
     o[7] = s.w.x; o[8] = s.w.y; o[9] = s.w.z;
     o[10] = s.v.x; o[11] = s.v.y; o[12] = s.v.z;
   }
+}
+
+template <bool FUSED, int NWARPS, int MINB, int SYNC, int SPLIT, int CMAX>
+__global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a) {
+  __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t edge_bars[2 * MBD_MAXL];
+  extern __shared__ __align__(16) float dyn[];
+  rollout_wpl_body<FUSED, SYNC, SPLIT, CMAX>(a, sblob, &mbar, edge_bars, dyn);
 }
 
 // ---- car2d (/root/reference/mbd/envs/car2d.py) ---------------------------------------------------------
@@ -581,6 +588,97 @@ __global__ void k_update(const float* __restrict__ partials, int P, int HNu, con
   out[j] = Yim1 / c_sqrt_abm1;
 }
 
+
+
+// ---- ONE kernel per diffusion step (single GPU, no demo): rollouts + statistics + weighted mean + update ------
+// reverse_once (mbd_planner.py:97-135) as a single cooperative launch: the rollout body above, a grid barrier,
+// then every CTA recomputes the global reward statistics redundantly (so no broadcast barrier is needed),
+// CTA r reduces run r of the weighted mean, a second grid barrier, and the first CTAs finish the pairwise tree
+// and the update.  The arithmetic replays k_softmax_weights / k_wsum_runs / k_wsum_tree / k_update exactly
+// (the 1024-thread strided partial sums + butterfly of k_softmax_weights are emulated with 1024 virtual threads and
+// an adjacent-pairwise shared-memory tree, which is the same association), so the fused step is bit-identical
+// to the multi-kernel path.
+struct StepTail {
+  float temp;
+  const float* Ybar_i;  // [HNu]
+  float c0, c1, c2, c3, c4;
+  float* weights;       // [n]
+  float* scalars;       // [4]
+  float* runs;          // [ceil(n/64)][HNu]
+  float* out;           // [HNu]
+};
+
+template <int OP, class F>
+__device__ __forceinline__ float vreduce1024(float* vp, int N, F term) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int v = tid; v < kStatThreads; v += nt) {
+    float acc = OP == OP_SUM ? 0.0f : -INFINITY;
+    for (int i = v; i < N; i += kStatThreads) acc = term(acc, i);
+    vp[v] = acc;
+  }
+  __syncthreads();
+  for (int o = 1; o < kStatThreads; o <<= 1) {
+    for (int v = tid; v < kStatThreads; v += nt)
+      if ((v & (2 * o - 1)) == 0) vp[v] = OP == OP_SUM ? vp[v] + vp[v + o] : fmaxf(vp[v], vp[v + o]);
+    __syncthreads();
+  }
+  float r = vp[0];
+  __syncthreads();
+  return r;
+}
+
+template <int NWARPS, int MINB, int CMAX>
+__global__ void __launch_bounds__(32 * NWARPS, MINB) k_reverse_step_wpl(RolloutArgs a, StepTail t) {
+  __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t edge_bars[2 * MBD_MAXL];
+  __shared__ float vp[kStatThreads];
+  __shared__ float wrun[kRun];
+  extern __shared__ __align__(16) float dyn[];
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  rollout_wpl_body<true, 0, 1, CMAX>(a, sblob, &mbar, edge_bars, dyn);
+  __threadfence();
+  grid.sync();
+  // ---- mbd_planner.py:110-127 (k_softmax_weights replayed) ------------------------------------------------
+  const int N = a.n, tid = threadIdx.x, nt = blockDim.x;
+  const int HNu = a.H * reinterpret_cast<const int*>(sblob)[MBD_H_NU];
+  const float* rews = a.rews;
+  const float fN = (float)N;
+  const float rew_mean = vreduce1024<OP_SUM>(vp, N, [&](float acc, int i) { return acc + rews[i]; }) / fN;
+  float rew_std = sqrtf(vreduce1024<OP_SUM>(vp, N, [&](float acc, int i) { float d = rews[i] - rew_mean; return fmaf(d, d, acc); }) / fN);
+  rew_std = rew_std < 1e-4f ? 1.0f : rew_std;
+  auto logp = [&](int i) { return (rews[i] - rew_mean) / rew_std / t.temp; };
+  const float mx = vreduce1024<OP_MAX>(vp, N, [&](float acc, int i) { return fmaxf(acc, logp(i)); });
+  const float S = vreduce1024<OP_SUM>(vp, N, [&](float acc, int i) { return acc + mbd_expf(logp(i) - mx); });
+  if (blockIdx.x == 0 && tid == 0) { t.scalars[0] = rew_mean; t.scalars[1] = rew_std; t.scalars[2] = mx; t.scalars[3] = S; }
+  // ---- mbd_planner.py:128, run r = this CTA (k_wsum_runs replayed) ------------------------------------------------
+  const int nruns = (N + kRun - 1) / kRun;
+  if ((int)blockIdx.x < nruns) {
+    const int n0 = blockIdx.x * kRun, n1 = min(n0 + kRun, N);
+    if (tid < n1 - n0) {
+      float w = mbd_expf(logp(n0 + tid) - mx) / S;
+      wrun[tid] = w;
+      t.weights[n0 + tid] = w;
+    }
+    __syncthreads();
+    for (int j = tid; j < HNu; j += nt) {
+      float acc = wrun[0] * a.Y0s[(size_t)n0 * HNu + j];
+      for (int n = n0 + 1; n < n1; ++n) acc = fmaf(wrun[n - n0], a.Y0s[(size_t)n * HNu + j], acc);
+      t.runs[(size_t)blockIdx.x * HNu + j] = acc;
+    }
+  }
+  __threadfence();
+  grid.sync();
+  // ---- pairwise tree over the runs + mbd_planner.py:100,130-133 (k_wsum_tree, k_update replayed) ----------------
+  const int j = blockIdx.x * nt + tid;
+  if (j < HNu) {
+    float Ybar = tree_sum_rows(t.runs, nruns, HNu, j);
+    float Yi = t.Ybar_i[j] * t.c0;
+    float score = t.c1 * (-Yi + t.c0 * Ybar);
+    float Yim1 = t.c3 * (Yi + t.c2 * score);
+    t.out[j] = Yim1 / t.c4;
+  }
+}
 
 // ---- fused cross-GPU exchange over NVLink peer memory ----------------------------------------------------
 // Replaces NCCL all_gather for the two tiny per-step exchanges (per-sample returns, rank partials):
@@ -863,6 +961,40 @@ int mbd_sample_rollout(const mbd_model* m, const float* state_init_dev, const ui
   a.rews = rews_dev; a.xref = xref_dev; a.href = href; a.logpd = logpd_dev;
   a.k0 = key[0]; a.k1 = key[1]; a.n_total = n_total; a.n_begin = n_begin; a.sigma = sigma; a.Ybar = Ybar_dev;
   return launch_rollout(true, a, m, (cudaStream_t)s);
+}
+
+int mbd_reverse_step(const mbd_model* m, const float* state_init_dev, const uint32_t key[2], int n, int H, float sigma,
+                     const float* Ybar_i_dev, float temp, const float coef[5], float* Y0s_dev, float* rews_dev, float* weights_dev,
+                     float* scalars_dev, float* runs_dev, float* Ybar_im1_dev, mbd_stream s) {
+  if (!m || !state_init_dev || !key || !Ybar_i_dev || !coef || !Y0s_dev || !rews_dev || !weights_dev || !scalars_dev || !runs_dev ||
+      !Ybar_im1_dev || n <= 0 || H <= 0)
+    return MBD_EINVAL;
+  if ((uint64_t)n * (uint64_t)H * (uint64_t)m->nu >= 0xffffffffull) return MBD_EINVAL;
+  // the single-kernel step exists for the one-link-per-warp mapping of 11-link models with <= 2 contacts per link
+  if (m->L != 11 || m->max_ncon > 2 || g_kernel_variant == 1) return MBD_EUNSUPPORTED;
+  const int grid = (n + mbd::kWplLanes - 1) / mbd::kWplLanes;
+  const size_t dyn = (size_t)m->L * (mbd::kXF + mbd::kEF) * mbd::kWplLanes * sizeof(float);
+  static int max_coresident = -1;
+  if (max_coresident < 0) {
+    int per_sm = 0, dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mbd::k_reverse_step_wpl<11, 2, 2>, 32 * 11, dyn));
+    max_coresident = per_sm * sms;
+  }
+  if (grid > max_coresident || grid * mbd::kWplLanes < 2048) return MBD_EUNSUPPORTED;  // needs co-residency; tiny shards use v1
+  mbd::RolloutArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->blob_dev; a.state_init = state_init_dev; a.Y0s = Y0s_dev; a.n = n; a.H = H; a.rews = rews_dev;
+  a.k0 = key[0]; a.k1 = key[1]; a.n_total = n; a.n_begin = 0; a.sigma = sigma; a.Ybar = Ybar_i_dev;
+  memcpy(a.wl, m->wl1, sizeof(a.wl));
+  a.offs = m->offs1;
+  mbd::StepTail t;
+  t.temp = temp; t.Ybar_i = Ybar_i_dev; t.c0 = coef[0]; t.c1 = coef[1]; t.c2 = coef[2]; t.c3 = coef[3]; t.c4 = coef[4];
+  t.weights = weights_dev; t.scalars = scalars_dev; t.runs = runs_dev; t.out = Ybar_im1_dev;
+  void* args[] = {&a, &t};
+  CK(cudaLaunchCooperativeKernel((const void*)mbd::k_reverse_step_wpl<11, 2, 2>, dim3(grid), dim3(32 * 11), args, dyn, (cudaStream_t)s));
+  return MBD_OK;
 }
 
 int mbd_car2d_rollout(const float* params_dev, const float* x0_dev, const uint32_t* key, int n_total, int n_begin, int n_local, int H,

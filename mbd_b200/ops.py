@@ -110,6 +110,24 @@ def sample_rollout(model: Model, state_init, key, n_total, n_begin, n_local, H, 
                                         _stream()), "mbd_sample_rollout")
 
 
+EUNSUPPORTED = -4
+
+
+def reverse_step(model: Model, state_init, key, n, H, sigma, Ybar_i, temp, coef, Y0s_out, rews_out, weights_out, scalars_out,
+                 runs_scratch, out) -> bool:
+    """reverse_once as ONE cooperative kernel.  Returns False when the configuration is not covered by the
+    fused kernel (the caller then issues the separate launches)."""
+    k, kp = key_ptr(key)
+    c = (ctypes.c_float * 5)(*[float(v) for v in coef])
+    rc = _lib.lib().mbd_reverse_step(model.handle, _p(_dev(state_init)), kp, n, H, ctypes.c_float(sigma), _p(_dev(Ybar_i)),
+                                     ctypes.c_float(temp), c, _p(_dev(Y0s_out)), _p(_dev(rews_out)), _p(_dev(weights_out)),
+                                     _p(_dev(scalars_out)), _p(_dev(runs_scratch)), _p(_dev(out)), _stream())
+    if rc == EUNSUPPORTED:
+        return False
+    check(rc, "mbd_reverse_step")
+    return True
+
+
 def car2d_rollout(params, x0, Y0s, xref=None, want_rewss=False, want_traj=False, key=None, n_total=0, n_begin=0,
                   sigma=0.0, Ybar=None, rews_out=None, logpd_out=None):
     """Car2d rollouts; with `key` the noise is drawn in-kernel and written to Y0s [n,H,2]."""

@@ -97,6 +97,13 @@ class DiffusionEngine:
         self.partials = self.partial if self.P == 1 else torch.empty((self.P, self.HNu), **f)
         self.Ybar_out = torch.empty(self.HNu, **f)
         self.launches_per_step = 5  # sample_rollout, softmax_weights, wsum_runs, wsum_tree, update
+        self.launches_last_step = 5
+        # ONE cooperative kernel per diffusion step (mbd_reverse_step; 1 GPU, no demo, Brax env) is available with
+        # MBD_SINGLE_KERNEL=1.  It is bit-identical but measured 2 % SLOWER than the five launches (1.581 vs 1.551 ms
+        # at 8192x50: every CTA recomputes the global statistics after the grid barrier, which costs more than the
+        # four launch gaps it removes), so the separate launches stay the default.
+        self.single_kernel = (self.P == 1 and not self.enable_demo and env.kind == "xpbd"
+                              and os.environ.get("MBD_SINGLE_KERNEL", "0") == "1")
         if env.kind == "xpbd":
             self.model = env.device_model(d)
             raw = state_init.pipeline_state.raw if hasattr(state_init, "pipeline_state") else state_init
@@ -161,6 +168,14 @@ class DiffusionEngine:
 
     def reverse_once(self, key, sigma: float, Ybar_i: torch.Tensor, coef, out: Optional[torch.Tensor] = None):
         """One diffusion step.  Returns (Ybar_im1 [HNu] device tensor, rews.mean() device scalar view)."""
+        if self.single_kernel:
+            out_t = self.Ybar_out if out is None else out
+            if ops.reverse_step(self.model, self.state_init, key, self.n_local, self.H, float(sigma), Ybar_i, self.temp, coef, self.Y0s,
+                                self.rews_local, self.weights, self.scalars, self.run_scratch, out_t):
+                self.launches_last_step = 1
+                return out_t, self.scalars[0]
+            self.single_kernel = False   # configuration not covered: stay on the separate launches
+        self.launches_last_step = self.launches_per_step
         self.rollout_phase(key, sigma, Ybar_i)
         self.gather_phase()
         out = self.reduce_phase(Ybar_i, coef, out)

@@ -203,3 +203,38 @@ def test_run_path_integral_cli_surface(capsys):
     assert mus.shape == (5, 50, 2) and np.isfinite(rf) and "override temp_sample" in capsys.readouterr().out
     with pytest.raises(KeyError):
         run_path_integral(PArgs(env_name="car2d", Nsample=64, Nrefine=3, update_method="nope"))
+
+
+@pytest.mark.parametrize("Nn", [2048, 8192])
+def test_single_kernel_step_equals_separate_launches(humanoidrun_setup, Nn, monkeypatch):
+    """mbd_reverse_step (ONE cooperative kernel per diffusion step) is bit-identical to the five-launch path."""
+    env, blob, st = humanoidrun_setup
+    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 300)
+    coef = eng.update_coef(alphas, alphas_bar, 200)
+    key = np.uint32([8, 9]); Ybar_i = torch.as_tensor((np.random.default_rng(1).normal(size=850) * 0.1).astype(np.float32), device=DEV)
+    monkeypatch.setenv("MBD_SINGLE_KERNEL", "0")
+    e0 = eng.DiffusionEngine(env, Nn, 50, 0.1, False, st)
+    ref, rew0 = e0.reverse_once(key, float(sigmas[200]), Ybar_i, coef)
+    assert not e0.single_kernel and e0.launches_last_step == 5
+    monkeypatch.setenv("MBD_SINGLE_KERNEL", "1")
+    e1 = eng.DiffusionEngine(env, Nn, 50, 0.1, False, st)
+    out, rew1 = e1.reverse_once(key, float(sigmas[200]), Ybar_i, coef)
+    assert e1.single_kernel and e1.launches_last_step == 1
+    assert_bit_exact(N(e1.rews_local), N(e0.rews_local)); assert_bit_exact(N(e1.Y0s), N(e0.Y0s))
+    assert_bit_exact(N(e1.weights), N(e0.weights), "weights"); assert_bit_exact(N(e1.scalars), N(e0.scalars), "scalars")
+    assert_bit_exact(N(out), N(ref), "Ybar_im1")
+    # second step on the evolved iterate (exercises buffer reuse)
+    out2, _ = e1.reverse_once(np.uint32([1, 1]), float(sigmas[199]), out.clone(), eng.update_coef(alphas, alphas_bar, 199))
+    ref2, _ = e0.reverse_once(np.uint32([1, 1]), float(sigmas[199]), ref.clone(), eng.update_coef(alphas, alphas_bar, 199))
+    assert_bit_exact(N(out2), N(ref2), "second step")
+
+
+def test_single_kernel_step_falls_back(humanoidrun_setup):
+    """tiny shards (v1 kernel territory) and the demo branch are not covered: the engine uses the separate launches"""
+    env, blob, st = humanoidrun_setup
+    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 100)
+    e = eng.DiffusionEngine(env, 256, 50, 0.1, False, st)
+    e.reverse_once(np.uint32([1, 2]), float(sigmas[50]), torch.zeros(850, device=DEV), eng.update_coef(alphas, alphas_bar, 50))
+    assert not e.single_kernel and e.launches_last_step == 5
+    t = mbd_b200.envs.get_env("humanoidtrack")
+    assert not eng.DiffusionEngine(t, 256, 50, 0.1, True, t.reset(None)).single_kernel
