@@ -229,11 +229,13 @@ def test_single_kernel_step_equals_separate_launches(humanoidrun_setup, Nn, monk
     assert_bit_exact(N(out2), N(ref2), "second step")
 
 
-def test_single_kernel_step_falls_back(humanoidrun_setup):
+def test_single_kernel_step_falls_back(humanoidrun_setup, monkeypatch):
     """tiny shards (v1 kernel territory) and the demo branch are not covered: the engine uses the separate launches"""
+    monkeypatch.setenv("MBD_SINGLE_KERNEL", "1")
     env, blob, st = humanoidrun_setup
     _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 100)
     e = eng.DiffusionEngine(env, 256, 50, 0.1, False, st)
+    assert e.single_kernel            # requested ...
     e.reverse_once(np.uint32([1, 2]), float(sigmas[50]), torch.zeros(850, device=DEV), eng.update_coef(alphas, alphas_bar, 50))
     assert not e.single_kernel and e.launches_last_step == 5
     t = mbd_b200.envs.get_env("humanoidtrack")
