@@ -1072,6 +1072,14 @@ int mbd_test_arith(int op, const float* a_dev, const float* b_dev, float* out_de
   return MBD_OK;
 }
 
+#ifdef MBD_PROFILE_PHASES
+int mbd_prof_read(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16 * 8); }
+int mbd_prof_reset(void) {
+  static unsigned long long z[16 * 8] = {0};
+  return (int)cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+}
+#endif
+
 int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5], float* Ybar_im1_dev,
                mbd_stream s) {
   if (!partials_dev || !Ybar_i_dev || !coef || !Ybar_im1_dev || P <= 0 || HNu <= 0) return MBD_EINVAL;

@@ -18,6 +18,17 @@
 
 #include "xpbd_device.cuh"
 
+// Optional per-phase clock64 accounting (scripts/gpu_phase_prof.py builds with -DMBD_PROFILE_PHASES; the
+// product build compiles these macros to nothing).  Slots per link: A, wait, B, wait, C, wait, D, wait.
+#ifdef MBD_PROFILE_PHASES
+__device__ unsigned long long g_phase_cycles[16][8];
+#define MBD_PH_BEGIN unsigned long long tprev_ = clock64();
+#define MBD_PH(i) { unsigned long long t_ = clock64(); if (S.lane == 0) atomicAdd(&g_phase_cycles[c.l][i], t_ - tprev_); tprev_ = t_; }
+#else
+#define MBD_PH_BEGIN
+#define MBD_PH(i)
+#endif
+
 namespace mbd {
 
 constexpr int kWplLanes = 32;
@@ -189,6 +200,7 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
   const bool has_parent = c.parent >= 0;
   const v3 p_prev = s.p;
   const q4 q_prev = s.q;  // x_i_prev
+  MBD_PH_BEGIN
 
   // ---- A: joints.acceleration_update ----------------------------------------------------------
   v3 T = V3(0.0f, 0.0f, 0.0f);
@@ -224,8 +236,10 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     T = vrotate(tq, a_p);
     S.put_e3(c.l, 0, T);
   }
+  MBD_PH(0)
   Y.arrive_terms(c.l);
   Y.phase_end();
+  MBD_PH(1)
   // ---- B: gather reaction torques, integrator.integrate_xdd, publish pose ---------------------------
   Y.wait_terms(c.child);
   {
@@ -240,9 +254,11 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     S.put_p(c.l, s.p);
     S.put_q(c.l, s.q);
   }
+  MBD_PH(2)
   Y.arrive_pose(c.l);
   const v3 w_before = s.w, v_before = s.v;
   Y.phase_end();
+  MBD_PH(3)
   // ---- C: joints.position_update ---------------------------------------------------------------------
   v3 dpc = V3(0.0f, 0.0f, 0.0f);
   q4 dqc = Q4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -299,8 +315,10 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     S.put_e3(c.l, 0, vscale(dp_p, M.hf(MBD_H_SCALE_POS)));
     S.put_e4(c.l, 3, qadd(qscale(dq_p, M.hf(MBD_H_SCALE_POS)), qscale(dqa_p, M.hf(MBD_H_SCALE_ANG))));
   }
+  MBD_PH(4)
   Y.arrive_terms(c.l);
   Y.phase_end();
+  MBD_PH(5)
   // ---- D: gather child deltas, apply; contacts; project_xd; contact velocities; publish q,w ----------
   Y.wait_terms(c.child);
   {
@@ -347,8 +365,10 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
   }
   S.put_q(c.l, s.q);
   S.put_w(c.l, s.w);
+  MBD_PH(6)
   Y.arrive_pose(c.l);
   Y.phase_end();
+  MBD_PH(7)
 }
 
 __device__ __forceinline__ v3 link_origin_w(const ModelSmem& M, int l, const LinkState& s) {

@@ -1,9 +1,12 @@
-"""Per-phase cycle accounting of the v2 rollout kernel (instrumented build scripts/libmbd_prof.so)."""
+"""Per-phase cycle accounting of the v2 rollout kernel (instrumented build: run `python -m` nothing else needed, it compiles scripts/libmbd_prof.so itself; needs nvcc)."""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from mbd_b200 import build as b
+# instrumented build of the same sources (-DMBD_PROFILE_PHASES), kept apart from the product library
 b.OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmbd_prof.so")
+b.NVCC_FLAGS = b.NVCC_FLAGS + ["-DMBD_PROFILE_PHASES"]
+b.build(force=True)
 b.is_stale = lambda: False
 import mbd_b200
 from mbd_b200 import ops, prng, _lib
@@ -15,7 +18,7 @@ L = _lib.lib()
 key = np.uint32([1, 2])
 names = env.sys.link_names
 for n in (32, 8192):
-    for v in (3, 2):
+    for v in (2, 3):
         ops.set_kernel_variant(v)
         Y0s = torch.empty((n, 850), device="cuda:0"); rews = torch.empty(n, device="cuda:0"); Yb = torch.zeros(850, device="cuda:0")
         ops.sample_rollout(m, st, key, n, 0, n, 50, 0.88, Yb, Y0s, rews); torch.cuda.synchronize()
