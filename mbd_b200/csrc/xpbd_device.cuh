@@ -57,12 +57,15 @@ __device__ __forceinline__ q4 vqmul(v3 a, q4 q) {
             fmaf(a.z, q.x, fmaf(a.y, q.w, -(a.x * q.z))),
             fmaf(a.z, q.w, fmaf(-a.y, q.x, a.x * q.y)));
 }
+// Oracle form: t = 2(u x v); c = u x t; r = fma(w, t, v) + c.  Scaling by 2 is exact, so with t' = u x v and
+// c' = u x t' (both exactly half of t, c):  fma(w, t, v) = fma(2w, t', v)  and  (.) + c = fma(2, c', (.))  — the same
+// two roundings on the same real values, two instructions fewer.  Bit-identical to oracle/mbd_oracle.c::vrotate.
 __device__ __forceinline__ v3 vrotate(v3 v, q4 q) {
   v3 u = V3(q.x, q.y, q.z);
   v3 t = vcross(u, v);
-  t = vadd(t, t);
   v3 c = vcross(u, t);
-  return V3(fmaf(q.w, t.x, v.x) + c.x, fmaf(q.w, t.y, v.y) + c.y, fmaf(q.w, t.z, v.z) + c.z);
+  float w2 = q.w + q.w;
+  return V3(fmaf(2.0f, c.x, fmaf(w2, t.x, v.x)), fmaf(2.0f, c.y, fmaf(w2, t.y, v.y)), fmaf(2.0f, c.z, fmaf(w2, t.z, v.z)));
 }
 __device__ __forceinline__ v3 vinv_rotate(v3 v, q4 q) { return vrotate(v, qconj(q)); }
 __device__ __forceinline__ q4 qnormalize(q4 q) {
@@ -119,7 +122,7 @@ __device__ __forceinline__ void contact_position_plane(const ModelSmem& M, int l
   float w = im + fmaf(r.x, r.x, r.y * r.y);
   float dl = coll ? MBD_DIV(-dist, w + 1e-6f) : 0.0f;
   dp.z = dp.z + dl * im;
-  dq = qadd(dq, qscale(vqmul_xy(r.y * dl, -(r.x * dl), q), 0.5f));
+  dq = qadd(dq, vqmul_xy(r.y * dl, -(r.x * dl), q));  // the factor 0.5 is applied once by the caller (exact scaling)
   // static friction: cancel the tangential travel of the contact point since x_i_prev
   v3 rl = vinv_rotate(r, q);
   v3 pbar = vadd(p_prev, vrotate(rl, q_prev));
@@ -135,7 +138,7 @@ __device__ __forceinline__ void contact_position_plane(const ModelSmem& M, int l
   float ptx = ntx * m, pty = nty * m;
   dp.x = dp.x + ptx * im;
   dp.y = dp.y + pty * im;
-  dq = qadd(dq, qscale(vqmul(V3(-(r.z * pty), r.z * ptx, fmaf(r.x, pty, -(r.y * ptx))), q), 0.5f));
+  dq = qadd(dq, vqmul(V3(-(r.z * pty), r.z * ptx, fmaf(r.x, pty, -(r.y * ptx))), q));
   dl_out = dl;
   cp_out = cp;
 }
@@ -311,9 +314,10 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     float dl = MBD_DIV(-cn, w_p + w_c + 1e-6f);
     v3 P = vscale(n, dl);
     v3 dp_c = vscale(P, im_c);
-    q4 dq_c = qscale(vqmul(vcross(rcw, P), s.q), 0.5f);
+    // the exact factors 0.5 (and ii_p in {0,1}) are folded into the scale constants below: (x*0.5)*s == x*(0.5*s) bit for bit
+    q4 dq_c = vqmul(vcross(rcw, P), s.q);
     v3 dp_p = vscale(P, -im_p);
-    q4 dq_p = qscale(vqmul(vcross(rpw, P), qp), -0.5f * ii_p);
+    q4 dq_p = vqmul(vcross(rpw, P), qp);
     q4 a_p = qmul(qp, c.pq);
     q4 a_c = qmul(s.q, c.jq);
     q4 j = qmul(qconj(a_p), a_c);
@@ -334,12 +338,13 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     float nn = vdot(na, na);
     float dla = MBD_DIV(-th, fmaf(ii_p, nn, nn) + 1e-6f);
     v3 Pa = vscale(na, dla);
-    q4 dqa_c = qscale(vqmul(Pa, s.q), 0.5f);
-    q4 dqa_p = qscale(vqmul(Pa, qp), -0.5f * ii_p);
+    q4 dqa_c = vqmul(Pa, s.q);
+    q4 dqa_p = vqmul(Pa, qp);
+    const float hsp = 0.5f * K.scale_pos, hsa = 0.5f * K.scale_ang;
     dpc = vscale(dp_c, K.scale_pos);
     dpp = vscale(dp_p, K.scale_pos);
-    dqc = qadd(qscale(dq_c, K.scale_pos), qscale(dqa_c, K.scale_ang));
-    dqp = qadd(qscale(dq_p, K.scale_pos), qscale(dqa_p, K.scale_ang));
+    dqc = qadd(qscale(dq_c, hsp), qscale(dqa_c, hsa));
+    dqp = qadd(qscale(dq_p, -hsp * ii_p), qscale(dqa_p, -hsa * ii_p));
   }
   {
     v3 dp = dpc;
@@ -368,7 +373,7 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     for (int ci = 0; ci < CMAX; ++ci)
       if (ci < c.ncon) contact_position_plane(M, c.l, ci, c.inv_mass, p0, q0, prev.p, prev.q, dp, dq, dlam[ci], cpos[ci]);
     s.p = vfma(dp, K.collide_scale, s.p);
-    s.q = qnormalize(qadd(s.q, qscale(dq, K.collide_scale)));
+    s.q = qnormalize(qadd(s.q, qscale(dq, 0.5f * K.collide_scale)));
   }
   // ---- integrator.project_xd -----------------------------------------------------------------------
   {

@@ -279,9 +279,10 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     float dl = MBD_DIV(-cn, w_p + w_c + 1e-6f);
     v3 P = vscale(n, dl);
     v3 dp_c = vscale(P, im_c);
-    q4 dq_c = qscale(vqmul(vcross(rcw, P), s.q), 0.5f);
+    // the exact factors 0.5 (and ii_p in {0,1}) are folded into the scale constants below: (x*0.5)*s == x*(0.5*s) bit for bit
+    q4 dq_c = vqmul(vcross(rcw, P), s.q);
     v3 dp_p = vscale(P, -im_p);
-    q4 dq_p = qscale(vqmul(vcross(rpw, P), qp), -0.5f * ii_p);
+    q4 dq_p = vqmul(vcross(rpw, P), qp);
     q4 a_p = qmul(qp, M.l4(MBD_F_PQ, c.l));
     q4 a_c = qmul(s.q, M.l4(MBD_F_JQ, c.l));
     q4 j = qmul(qconj(a_p), a_c);
@@ -308,12 +309,13 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     float nn = vdot(na, na);
     float dla = MBD_DIV(-th, fmaf(ii_p, nn, nn) + 1e-6f);
     v3 Pa = vscale(na, dla);
-    q4 dqa_c = qscale(vqmul(Pa, s.q), 0.5f);
-    q4 dqa_p = qscale(vqmul(Pa, qp), -0.5f * ii_p);
+    q4 dqa_c = vqmul(Pa, s.q);
+    q4 dqa_p = vqmul(Pa, qp);
+    const float hsp = 0.5f * M.hf(MBD_H_SCALE_POS), hsa = 0.5f * M.hf(MBD_H_SCALE_ANG);
     dpc = vscale(dp_c, M.hf(MBD_H_SCALE_POS));
-    dqc = qadd(qscale(dq_c, M.hf(MBD_H_SCALE_POS)), qscale(dqa_c, M.hf(MBD_H_SCALE_ANG)));
+    dqc = qadd(qscale(dq_c, hsp), qscale(dqa_c, hsa));
     S.put_e3(c.l, 0, vscale(dp_p, M.hf(MBD_H_SCALE_POS)));
-    S.put_e4(c.l, 3, qadd(qscale(dq_p, M.hf(MBD_H_SCALE_POS)), qscale(dqa_p, M.hf(MBD_H_SCALE_ANG))));
+    S.put_e4(c.l, 3, qadd(qscale(dq_p, -hsp * ii_p), qscale(dqa_p, -hsa * ii_p)));
   }
   MBD_PH(4)
   Y.arrive_terms(c.l);
@@ -344,7 +346,7 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
       if (ci < c.ncon) contact_position_plane(M, c.l, ci, M.lf(MBD_F_INV_MASS, c.l), p0, q0, p_prev, q_prev, dp, dq, dlam[ci], cpos[ci]);
     }
     s.p = vfma(dp, M.hf(MBD_H_COLLIDE_SCALE), s.p);
-    s.q = qnormalize(qadd(s.q, qscale(dq, M.hf(MBD_H_COLLIDE_SCALE))));
+    s.q = qnormalize(qadd(s.q, qscale(dq, 0.5f * M.hf(MBD_H_COLLIDE_SCALE))));
   }
   {
     s.v = vscale(vsub(s.p, p_prev), M.hf(MBD_H_INV_DT));
