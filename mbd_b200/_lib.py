@@ -28,9 +28,12 @@ def lib():
     if _LIB is not None:
         return _LIB
     path = _build.OUT
-    if not os.path.exists(path) or _build.is_stale():
+    # Build only when the library is MISSING (a fresh clone).  A copied tree can carry arbitrary mtimes, and N ranks
+    # starting together must never race to rewrite the same .so; staleness is handled by `python -m mbd_b200.build`
+    # / __graft_entry__.build(), or by setting MBD_REBUILD=1.
+    if not os.path.exists(path) or (os.environ.get("MBD_REBUILD") == "1" and _build.is_stale()):
         try:
-            path = _build.build()
+            path = _build.build(force=True)
         except Exception as e:  # noqa: BLE001
             if not os.path.exists(path):
                 raise MbdError(f"libmbd_b200.so is missing and could not be built ({e}); there is no CPU fallback") from e
