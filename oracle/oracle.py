@@ -19,12 +19,20 @@ _u32p = ctypes.POINTER(ctypes.c_uint32)
 
 
 def build(force: bool = False) -> str:
+    """Compiles oracle/libmbd_oracle.so (gcc, see oracle/Makefile) when it is missing, stale or forced."""
+    import fcntl
     so = os.path.join(_HERE, "libmbd_oracle.so")
     src = os.path.join(_HERE, "mbd_oracle.c")
     hdrs = [os.path.join(_HERE, "..", "include", h) for h in ("mbd_fp32.h", "mbd_model.h")]
-    stale = (not os.path.exists(so)) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in [src] + hdrs if os.path.exists(p))
-    if force or stale:
-        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+
+    def stale():
+        return (not os.path.exists(so)) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in [src] + hdrs if os.path.exists(p))
+
+    if force or stale():
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if force or stale():
+                subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return so
 
 
