@@ -1,0 +1,44 @@
+"""env-steps/s of one diffusion step for every BASELINE.json config this repo can run (1 GPU), with the
+per-sample returns of the first 32 samples checked bit for bit against the CPU oracle."""
+import os, sys, json
+import numpy as np, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import mbd_b200
+from mbd_b200 import prng
+from mbd_b200.planners import engine as eng
+from oracle import oracle as orc
+
+CONFIGS = [("car2d", 64, 40, False, 100), ("car2d", 2048, 50, True, 100), ("humanoidrun", 8192, 50, False, 300),
+           ("humanoidtrack", 16384, 50, True, 100), ("humanoidtrack", 16384, 60, True, 100), ("humanoidstandup", 8192, 50, False, 100)]
+rows = []
+for name, N, H, demo, Nd in CONFIGS:
+    env = mbd_b200.envs.get_env(name)
+    rng, rr = prng.split(prng.PRNGKey(0))
+    st = env.reset(rr)
+    _, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, Nd)
+    e = eng.DiffusionEngine(env, N, H, 0.1, demo, st)
+    Nu = env.action_size
+    Yb = torch.zeros(H * Nu, device="cuda:0"); out = torch.empty(H * Nu, device="cuda:0")
+    key = np.uint32([5, 7]); i = Nd - 1
+    for _ in range(3):
+        e.reverse_once(key, float(sigmas[i]), Yb, eng.update_coef(alphas, alphas_bar, i), out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = 20
+    e0.record()
+    for _ in range(K):
+        e.reverse_once(key, float(sigmas[i]), Yb, eng.update_coef(alphas, alphas_bar, i), out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    Y = e.Y0s[:32].cpu().numpy().reshape(32, H, Nu)
+    if env.kind == "xpbd":
+        ref = orc.xpbd_rollout(env.blob, st.pipeline_state.raw, Y, xref=env.xref if demo else None)
+    else:
+        ref = orc.car2d_rollout(env.params, env.x0, Y, xref=env.xref if demo else None)
+    ok = np.array_equal(e.rews_local[:32].cpu().numpy().view(np.uint32), ref["rews"].view(np.uint32))
+    if demo:
+        ok = ok and np.array_equal(e.logpd_local[:32].cpu().numpy().view(np.uint32), ref["logpd"].view(np.uint32))
+    rows.append(dict(env=name, Nsample=N, Hsample=H, demo=demo, ms_per_step=ms, env_steps_per_s=N * H / ms * 1e3, oracle_bit_exact=bool(ok)))
+    print(rows[-1])
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(rows, open("gpurun_out/configs_r01.json", "w"), indent=1)
