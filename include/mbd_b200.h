@@ -96,6 +96,11 @@ int mbd_softmax_weights(const float* rews_all_dev, const float* logpd_all_dev, i
 int mbd_weighted_sum(const float* weights_dev, const float* Y0s_dev, int n_local, int HNu, float* scratch_dev,
                      float* partial_dev, mbd_stream s);
 
+/* First stage of mbd_weighted_sum only: runs_dev [ceil(n_local/64)][HNu].  Returns the number of runs (> 0) or a
+ * negative error.  With one rank the pairwise tree over the runs is the same tree mbd_update applies to its
+ * `partials`, so `mbd_update(runs, P = nruns, ...)` finishes the weighted mean and the update in one launch. */
+int mbd_weighted_sum_runs(const float* weights_dev, const float* Y0s_dev, int n_local, int HNu, float* runs_dev, mbd_stream s);
+
 /* einsum("n,nij->ij", weights, (Y0s - mu_0t)**2): the CMA-ES spread update of
  * /root/reference/mbd/planners/path_integral.py:39-45, same deterministic order as mbd_weighted_sum. */
 int mbd_weighted_sqerr_sum(const float* weights_dev, const float* Y0s_dev, const float* mu_dev, int n_local, int HNu,

@@ -1043,6 +1043,15 @@ int mbd_weighted_sum(const float* weights_dev, const float* Y0s_dev, int n_local
   return weighted_sum_impl(weights_dev, Y0s_dev, nullptr, n_local, HNu, scratch_dev, partial_dev, s);
 }
 
+int mbd_weighted_sum_runs(const float* weights_dev, const float* Y0s_dev, int n_local, int HNu, float* runs_dev, mbd_stream s) {
+  if (!weights_dev || !Y0s_dev || !runs_dev || n_local <= 0 || HNu <= 0) return MBD_EINVAL;
+  int nruns = (n_local + mbd::kRun - 1) / mbd::kRun;
+  dim3 grid(nruns, (HNu + 255) / 256);
+  mbd::k_wsum_runs<false><<<grid, 256, 0, (cudaStream_t)s>>>(weights_dev, Y0s_dev, nullptr, n_local, HNu, runs_dev);
+  CK(cudaGetLastError());
+  return nruns;
+}
+
 int mbd_weighted_sqerr_sum(const float* weights_dev, const float* Y0s_dev, const float* mu_dev, int n_local, int HNu, float* scratch_dev,
                            float* partial_dev, mbd_stream s) {
   if (!mu_dev) return MBD_EINVAL;

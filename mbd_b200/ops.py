@@ -162,6 +162,14 @@ def weighted_sum(weights, Y0s, HNu, scratch, partial_out):
                                       _stream()), "mbd_weighted_sum")
 
 
+def weighted_sum_runs(weights, Y0s, HNu, runs_out) -> int:
+    """first stage only; returns the number of 64-sample runs written to runs_out [nruns, HNu]"""
+    rc = _lib.lib().mbd_weighted_sum_runs(_p(_dev(weights)), _p(_dev(Y0s)), weights.numel(), HNu, _p(_dev(runs_out)), _stream())
+    if rc <= 0:
+        check(rc if rc < 0 else -1, "mbd_weighted_sum_runs")
+    return rc
+
+
 def weighted_sqerr_sum(weights, Y0s, mu, HNu, scratch, partial_out):
     n_local = weights.numel()
     check(_lib.lib().mbd_weighted_sqerr_sum(_p(_dev(weights)), _p(_dev(Y0s)), _p(_dev(mu)), n_local, HNu, _p(_dev(scratch)),

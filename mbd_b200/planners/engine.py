@@ -96,8 +96,10 @@ class DiffusionEngine:
         self.partial = self.sym[self.off_partial:self.off_partial + self.HNu] if self.sym is not None else torch.empty(self.HNu, **f)
         self.partials = self.partial if self.P == 1 else torch.empty((self.P, self.HNu), **f)
         self.Ybar_out = torch.empty(self.HNu, **f)
-        self.launches_per_step = 5  # sample_rollout, softmax_weights, wsum_runs, wsum_tree, update
-        self.launches_last_step = 5
+        # own kernels per step: sample_rollout, softmax_weights, wsum_runs, update (+ wsum_tree and, with the fused NVLink
+        # exchange, two k_peer_gather launches when sharded)
+        self.launches_per_step = 4 if self.P == 1 else (7 if self.sym is not None else 5)
+        self.launches_last_step = self.launches_per_step
         # ONE cooperative kernel per diffusion step (mbd_reverse_step; 1 GPU, no demo, Brax env) is available with
         # MBD_SINGLE_KERNEL=1.  It is bit-identical but measured 2 % SLOWER than the five launches (1.581 vs 1.551 ms
         # at 8192x50: every CTA recomputes the global statistics after the grid barrier, which costs more than the
@@ -151,6 +153,11 @@ class DiffusionEngine:
         out = self.Ybar_out if out is None else out
         ops.softmax_weights(self.rews_all, self.logpd_all, self.n_begin, self.n_local, self.temp, self.rew_xref, self.weights,
                             self.scalars, self.logp_scratch)
+        if self.P == 1:
+            # one rank: the tree over the 64-sample runs IS the rank tree of mbd_update — skip the separate tree launch
+            nruns = ops.weighted_sum_runs(self.weights, self.Y0s, self.HNu, self.run_scratch)
+            ops.update(self.run_scratch, nruns, self.HNu, Ybar_i, coef, out)
+            return out
         ops.weighted_sum(self.weights, self.Y0s, self.HNu, self.run_scratch, self.partial)
         if self.sym is not None:
             ops.peer_gather(self.peer_ptrs, self.P, self.rank, self.off_partial, self.HNu, self.off_flags + 8, self.epoch,

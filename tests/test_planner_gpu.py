@@ -215,7 +215,7 @@ def test_single_kernel_step_equals_separate_launches(humanoidrun_setup, Nn, monk
     monkeypatch.setenv("MBD_SINGLE_KERNEL", "0")
     e0 = eng.DiffusionEngine(env, Nn, 50, 0.1, False, st)
     ref, rew0 = e0.reverse_once(key, float(sigmas[200]), Ybar_i, coef)
-    assert not e0.single_kernel and e0.launches_last_step == 5
+    assert not e0.single_kernel and e0.launches_last_step == 4
     monkeypatch.setenv("MBD_SINGLE_KERNEL", "1")
     e1 = eng.DiffusionEngine(env, Nn, 50, 0.1, False, st)
     out, rew1 = e1.reverse_once(key, float(sigmas[200]), Ybar_i, coef)
@@ -237,6 +237,6 @@ def test_single_kernel_step_falls_back(humanoidrun_setup, monkeypatch):
     e = eng.DiffusionEngine(env, 256, 50, 0.1, False, st)
     assert e.single_kernel            # requested ...
     e.reverse_once(np.uint32([1, 2]), float(sigmas[50]), torch.zeros(850, device=DEV), eng.update_coef(alphas, alphas_bar, 50))
-    assert not e.single_kernel and e.launches_last_step == 5
+    assert not e.single_kernel and e.launches_last_step == 4
     t = mbd_b200.envs.get_env("humanoidtrack")
     assert not eng.DiffusionEngine(t, 256, 50, 0.1, True, t.reset(None)).single_kernel
