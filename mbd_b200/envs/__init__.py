@@ -1,5 +1,6 @@
 """Env registry — mirrors /root/reference/mbd/envs/__init__.py:13-33 (same names, same ValueError)."""
 from .car2d import Car2d
+from .generic import GenericPositionalEnv  # noqa: F401
 from .humanoidrun import HumanoidRun
 from .humanoidstandup import HumanoidStandup
 from .humanoidtrack import HumanoidTrack

@@ -90,3 +90,16 @@ def test_humanoidtrack_subset():
     assert i32[blob.H_NTRACK] == 5 and i32[blob.H_TRACK0:blob.H_TRACK0 + 5].tolist() == [0, 5, 3, 6, 4]
     with pytest.raises(NotImplementedError):
         blob.pack(s, 5, blob.REWARD_HUMANOIDTRACK)  # slide joints of the cosmetic bodies
+
+
+def test_generic_quadruped_fixture():
+    """a model outside the reference tree goes through the same compiler (GenericPositionalEnv's path)"""
+    s = mjcf.load(os.path.join(os.path.dirname(__file__), "fixtures", "quadruped.xml"))
+    assert s.link_types == "f11111111" and s.link_parents == [-1, 0, 1, 0, 3, 0, 5, 0, 7]
+    assert len(s.contacts) == 9 and s.act_size() == 8 and np.allclose(s.act_gear, 60.0)
+    b = blob.pack(s, 5, blob.REWARD_HUMANOIDRUN)
+    i32 = b.view(np.int32)
+    lf = lambda f, l: blob.HDR_WORDS + f * blob.MAXL + l
+    assert [i32[lf(blob.F_CHILD0 + c, 0)] for c in range(4)] == [1, 3, 5, 7]
+    assert i32[lf(blob.F_NCON, 0)] == 1 and i32[lf(blob.F_NCON, 2)] == 2
+    assert np.allclose(s.dof_limit[7], np.deg2rad([30, 70]))

@@ -163,6 +163,30 @@ def test_humanoidstandup_bit_exact(orc, variant):
     assert_bit_exact(N(out["rews"]), ref["rews"])
 
 
+@pytest.mark.parametrize("v", [1, 2])
+def test_generic_model_quadruped_bit_exact(orc, v):
+    """A model that is NOT one of the reference humanoids (9 links, root with 4 children, capsule feet): the generic
+    kernel instantiations (L != 11) of both mappings agree with the oracle bit for bit."""
+    from mbd_b200 import prng
+    env = mbd_b200.envs.GenericPositionalEnv(os.path.join(os.path.dirname(__file__), "fixtures", "quadruped.xml"), n_frames=5)
+    st = env.reset(prng.split(prng.PRNGKey(3))[1]).pipeline_state.raw
+    m = env.device_model(torch.device(DEV))
+    Y = _actions(np.random.default_rng(21), 70, 30, 8, 0.7)
+    ref = orc.xpbd_rollout(env.blob, st, Y, want_rewss=True, want_final=True)
+    ops.set_kernel_variant(v)
+    try:
+        out = ops.rollout(m, T(st), T(Y), want_rewss=True, want_final=True)
+    finally:
+        ops.set_kernel_variant(0)
+    assert_bit_exact(N(out["final"]), ref["final"]); assert_bit_exact(N(out["rews"]), ref["rews"])
+    # and the planner runs on it end to end
+    from mbd_b200.planners import engine as eng
+    _, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, 50)
+    e = eng.DiffusionEngine(env, 256, 30, 0.1, False, st)
+    o, rew = e.reverse_once(np.uint32([1, 2]), float(sigmas[40]), torch.zeros(240, device=DEV), eng.update_coef(alphas, alphas_bar, 40))
+    assert np.isfinite(N(o)).all() and np.isfinite(rew.item())
+
+
 def test_car2d_bit_exact(orc):
     car = mbd_b200.envs.get_env("car2d")
     params, xref = car.device_params()
