@@ -54,8 +54,8 @@ def pack(sys: System, n_frames: int, reward: int, links=None, track_links=(), re
     drops the 5 cosmetic, dynamically decoupled *_ref bodies)."""
     if sys.custom["spring_inertia_scale"] != 1.0:
         raise NotImplementedError("only spring_inertia_scale == 1 (identity rotational inertia) is supported")
-    if sys.custom["spring_mass_scale"] != 0.0:
-        raise NotImplementedError("only spring_mass_scale == 0 is supported")
+    # Brax positional: mass = link.inertia.mass ** (1 - spring_mass_scale)
+    mass_exp = 1.0 - float(sys.custom["spring_mass_scale"])
     if links is None:
         links = list(range(sys.num_links()))
     L = len(links)
@@ -114,9 +114,9 @@ def pack(sys: System, n_frames: int, reward: int, links=None, track_links=(), re
             raise NotImplementedError("too many children")
         for c, k in enumerate(sorted(kids)):
             i32[lf(F_CHILD0 + c, new)] = k
-        m = float(sys.mass[old])
+        m = float(sys.mass[old]) ** mass_exp
         f[lf(F_MASS, new)], f[lf(F_INV_MASS, new)] = m, 1.0 / m
-        f[lf(F_PINV_MASS, new)] = 1.0 / float(sys.mass[par_old]) if par_old >= 0 else 0.0
+        f[lf(F_PINV_MASS, new)] = 1.0 / (float(sys.mass[par_old]) ** mass_exp) if par_old >= 0 else 0.0
         f[lf(F_PINV_INERTIA, new)] = 1.0 if par_old >= 0 else 0.0
         com = sys.com[old]
         for a in range(3):

@@ -376,7 +376,8 @@ def load(path: str) -> System:
     cust = root.find("custom")
     if cust is not None:
         for n in cust.findall("numeric"):
-            custom[n.get("name")] = float(n.get("data").split()[0])
+            vals = [float(v) for v in n.get("data").split()]
+            custom[n.get("name")] = vals[0] if len(vals) == 1 else np.array(vals)
 
     bodies: List[Body] = []
     world_geoms: List[Geom] = []
@@ -503,5 +504,9 @@ def load(path: str) -> System:
         act_names=act_names, act_qd_id=np.array(act_qd, dtype=np.int64), act_q_id=np.array(act_q, dtype=np.int64),
         act_gear=np.array(act_gear), act_ctrl_range=np.array(act_ctrl).reshape(-1, 2), act_gain=np.array(act_gain),
         act_bias_q=np.array(act_bq), act_bias_qd=np.array(act_bqd),
-        geoms=all_geoms, contacts=contacts, dt=dt, gravity=gravity, init_q=np.array(init_q), custom=custom,
+        geoms=all_geoms, contacts=contacts, dt=dt, gravity=gravity,
+        # Brax: a <custom><numeric name="init_qpos"> overrides the MuJoCo qpos0
+        init_q=(np.asarray(custom["init_qpos"], dtype=np.float64) if isinstance(custom.get("init_qpos"), np.ndarray)
+                and len(custom["init_qpos"]) == len(init_q) else np.array(init_q)),
+        custom={k: v for k, v in custom.items() if not isinstance(v, np.ndarray)},
     )
