@@ -22,11 +22,12 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-env = mbd_b200.envs.get_env("humanoidrun")
+demo = os.environ.get("MBD_TEST_DEMO", "0") == "1"   # BASELINE config 5: humanoidtrack + enable_demo, sample-sharded
+env = mbd_b200.envs.get_env("humanoidtrack" if demo else "humanoidrun")
 rng, rr = prng.split(prng.PRNGKey(0))
 st = env.reset(rr)
 _, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, 100)
-e = eng.DiffusionEngine(env, 2048, 50, 0.1, False, st)
+e = eng.DiffusionEngine(env, 2048, 50, 0.1, demo, st)
 Yb = torch.zeros(850, device="cuda")
 key = np.uint32([3, 1])
 outs = []
@@ -49,10 +50,11 @@ def _port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_nccl_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("demo", ["0", "1"], ids=["humanoidrun", "humanoidtrack-demo"])
+def test_two_rank_nccl_equals_single_gpu(tmp_path, demo):
     w = tmp_path / "worker.py"
     w.write_text(WORKER)
-    env = dict(os.environ, MBD_ROOT=ROOT)
+    env = dict(os.environ, MBD_ROOT=ROOT, MBD_TEST_DEMO=demo)
     env1 = dict(env, MBD_OUT=str(tmp_path / "p1.npy"))
     subprocess.run([sys.executable, str(w)], check=True, env=env1, timeout=600)
     a = np.load(tmp_path / "p1.npy")
