@@ -32,7 +32,7 @@ const char* mbd_last_error(void);
 int mbd_device_count(void);
 /* rollout kernel mapping: 0 = auto (by shard size), 1 = v1 (one link per lane), 2/3/4 = v2 (one link per
  * warp, lane = sample) with CTA-wide / named-barrier / mbarrier phase synchronisation, 5 = v2 with two
- * same-type links per warp (16 samples per CTA).  All variants
+ * same-type links per warp (16 samples per CTA), 6 = v2 with two interleaved 32-sample groups per 704-thread CTA.  All variants
  * produce bit-identical results; the switch exists for tests and profiling. */
 int mbd_set_kernel_variant(int v);
 

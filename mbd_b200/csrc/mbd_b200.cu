@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
 }
 
 // ---- v2 rollout kernel: warp per link, lane per sample (xpbd_wpl.cuh) -------------------------------------
-template <bool FUSED, int SYNC, int SPLIT, int CMAX>
+template <bool FUSED, int SYNC, int SPLIT, int CMAX, int GROUPS = 1>
 __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sblob, uint64_t* mbar_p, uint64_t* edge_bars, float* dyn) {
   stage_model_tma(sblob, mbar_p, a.blob);
   ModelSmem M;
@@ -235,9 +235,14 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
 
   static_assert(SPLIT == 1 || SPLIT == 2, "links per warp");
   static_assert(SPLIT == 1 || SYNC == 0, "edge barriers assume one link per warp");
+  static_assert(GROUPS == 1 || (SPLIT == 1 && SYNC == 0), "sample groups: one link per warp, group barriers");
   constexpr int kLpl = kWplLanes / SPLIT;                      // lanes (= samples) per link
   const int tid = threadIdx.x, lane = tid & 31;
-  const int l = a.wl[tid >> 5][SPLIT == 1 ? 0 : lane / kLpl];  // warp (and half) -> link
+  // GROUPS independent 32-sample groups share the CTA with their warps INTERLEAVED (warp w -> group w % GROUPS,
+  // link slot w / GROUPS), so the links that the mapping marks critical (highest slots) have the highest warp ids
+  // of the whole CTA — the SM arbiter issues the highest eligible warp id first.
+  const int grp = (tid >> 5) % GROUPS;
+  const int l = a.wl[(tid >> 5) / GROUPS][SPLIT == 1 ? 0 : lane / kLpl];  // warp (and half) -> link
   const int slot = lane % kLpl;                                // sample index inside the CTA
   const int L = M.hi(MBD_H_NLINK), nu = M.hi(MBD_H_NU);
   const int HNu = a.H * nu;
@@ -248,8 +253,8 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
 
   if (FUSED) {
     const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
-    const int first = blockIdx.x * kLpl;
-    const int cnt = min(kLpl, a.n - first) * HNu;
+    const int first = blockIdx.x * kLpl * GROUPS;
+    const int cnt = min(kLpl * GROUPS, a.n - first) * HNu;
     for (int e = tid; e < cnt; e += nthreads) {
       int ns = first + e / HNu, j = e % HNu;
       uint32_t idx = (uint32_t)(a.n_begin + ns) * (uint32_t)HNu + (uint32_t)j;
@@ -259,8 +264,8 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
   }
 
   WplSmem S;
-  S.X = dyn;
-  S.E = dyn + L * kXF * kWplLanes;
+  S.X = dyn + grp * L * (kXF + kEF) * kWplLanes;
+  S.E = S.X + L * kXF * kWplLanes;
   S.lane = slot;
   S.offs = a.offs;
   // a thread whose half owns no link (odd link count) shadows its partner's link into the unused half of
@@ -270,7 +275,7 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
   WarpCfg c;
   load_warp_cfg(M, l, c);
 
-  const int n_local = blockIdx.x * kLpl + slot;
+  const int n_local = (blockIdx.x * GROUPS + grp) * kLpl + slot;
   const bool active = n_local < a.n && owner;
   const int n_rd = n_local < a.n ? n_local : a.n - 1;
 
@@ -283,7 +288,9 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
     s.v = V3(st[10], st[11], st[12]);
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
-  typename std::conditional<SYNC == 1, SyncP2P, typename std::conditional<SYNC == 2, SyncNamed, SyncCta>::type>::type Y;
+  typename std::conditional<GROUPS != 1, SyncGroup,
+      typename std::conditional<SYNC == 1, SyncP2P, typename std::conditional<SYNC == 2, SyncNamed, SyncCta>::type>::type>::type Y;
+  if constexpr (GROUPS != 1) { Y.id = 1 + grp; Y.count = 32 * L; }
   if constexpr (SYNC == 2) Y.setup(M, l, L);
   if constexpr (SYNC == 1) {
     Y.pose = edge_bars; Y.terms = edge_bars + MBD_MAXL; Y.ph_pose = 0u; Y.ph_terms = 0u;
@@ -363,13 +370,13 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
   }
 }
 
-template <bool FUSED, int NWARPS, int MINB, int SYNC, int SPLIT, int CMAX>
+template <bool FUSED, int NWARPS, int MINB, int SYNC, int SPLIT, int CMAX, int GROUPS = 1>
 __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a) {
   __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ __align__(8) uint64_t edge_bars[2 * MBD_MAXL];
   extern __shared__ __align__(16) float dyn[];
-  rollout_wpl_body<FUSED, SYNC, SPLIT, CMAX>(a, sblob, &mbar, edge_bars, dyn);
+  rollout_wpl_body<FUSED, SYNC, SPLIT, CMAX, GROUPS>(a, sblob, &mbar, edge_bars, dyn);
 }
 
 // ---- car2d (/root/reference/mbd/envs/car2d.py) ---------------------------------------------------------
@@ -826,7 +833,7 @@ int mbd_device_count(void) {
 }
 
 int mbd_set_kernel_variant(int v) {
-  if (v < 0 || v > 5) return MBD_EINVAL;
+  if (v < 0 || v > 6) return MBD_EINVAL;
   g_kernel_variant = v;
   return MBD_OK;
 }
@@ -903,7 +910,8 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   // auto: small shards keep more warps in flight with the lane-per-link kernel; large ones use v2
   // (measured, humanoidrun): < 2048 samples v1 keeps more warps in flight; one CTA per SM favours the
   // named edge barriers; two CTAs per SM (> 148 CTAs) favour plain CTA barriers (better I-cache locality)
-  if (variant == 0) variant = (L == 11) ? (a.n < 2048 ? 1 : (a.n <= 148 * 32 ? 3 : 2)) : 2;
+  // beyond one 32-sample CTA per SM: two interleaved groups per 704-thread CTA (critical links get the highest warp ids)
+  if (variant == 0) variant = (L == 11) ? (a.n < 2048 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 6 : 2))) : 2;
   if (variant >= 2) {
     size_t dyn = (size_t)L * (mbd::kXF + mbd::kEF) * mbd::kWplLanes * sizeof(float);
     const bool split = (variant == 5);
@@ -915,7 +923,18 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
       else MBD_LAUNCH_WPL(MBD_MAXL, 1, 0, 2, grid, 32 * nw);
     } else {
       int grid = (a.n + mbd::kWplLanes - 1) / mbd::kWplLanes;
-      if (L == 11 && variant == 2) MBD_LAUNCH_WPL(11, 2, 0, 1, grid, 32 * L);       // CTA-wide barriers
+      if (L == 11 && variant == 6 && m->max_ncon <= 2) {  // two interleaved 32-sample groups per 704-thread CTA
+        int grid2 = (a.n + 63) / 64;
+        size_t dyn2 = 2 * dyn;
+        static bool attr_set = false;
+        if (!attr_set) {
+          CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+          CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+          attr_set = true;
+        }
+        if (fused) mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+        else mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+      } else if (L == 11 && variant == 2) MBD_LAUNCH_WPL(11, 2, 0, 1, grid, 32 * L);       // CTA-wide barriers
       else if (L == 11 && variant == 3 && grid <= 148) MBD_LAUNCH_WPL(11, 1, 2, 1, grid, 32 * L);  // one CTA per SM: no register cap
       else if (L == 11 && variant == 3) MBD_LAUNCH_WPL(11, 2, 2, 1, grid, 32 * L);  // named edge barriers
       else if (L == 11 && variant == 4) MBD_LAUNCH_WPL(11, 2, 1, 1, grid, 32 * L);  // mbarrier point-to-point

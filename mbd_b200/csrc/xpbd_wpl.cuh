@@ -102,6 +102,17 @@ struct SyncCta {
   __device__ __forceinline__ void phase_end() { __syncthreads(); }
 };
 
+// SyncGroup: a CTA that hosts G independent sample groups (warps interleaved) gives each group its own
+// hardware barrier id; semantics within a group are those of SyncCta.
+struct SyncGroup {
+  int id, count;
+  __device__ __forceinline__ void wait_pose(int) {}
+  __device__ __forceinline__ void arrive_terms(int) {}
+  __device__ __forceinline__ void wait_terms(const int*) {}
+  __device__ __forceinline__ void arrive_pose(int) {}
+  __device__ __forceinline__ void phase_end() { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+};
+
 struct SyncP2P {
   uint64_t* pose;   // [L]
   uint64_t* terms;  // [L]

@@ -36,7 +36,8 @@ def _dev(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
 
 def set_kernel_variant(v: int):
     """0 = auto, 1 = lane-per-link kernel, 2/3/4 = warp-per-link kernel with CTA / named / mbarrier sync,
-    5 = two links per warp / 16 samples per CTA (all bit-identical)."""
+    5 = two links per warp / 16 samples per CTA,
+    6 = two interleaved sample groups per CTA (all bit-identical)."""
     check(_lib.lib().mbd_set_kernel_variant(int(v)), "mbd_set_kernel_variant")
 
 
