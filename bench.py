@@ -256,7 +256,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": HNu * 4 + 8, "d2h_bytes_per_step": HNu * 4 + 4},
             "gpu_launches": e.launches_last_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": ("k_reverse_step_wpl (sampling + rollouts + statistics + weighted mean + update, one launch)"
-                                                   if e.single_kernel else "k_rollout_wpl<true> (fused sampling + rollouts)"), "achieved": achieved,
+                                                   if e.single_kernel else f"{_ncu_summary().get('kernel', 'k_rollout_wpl<true,...>')} (fused sampling + rollouts)"), "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_s * 1e3,
                          "note": "path is fp32-issue bound, not HBM bound (SURVEY F7): see DESIGN.md roofline section"},

@@ -35,6 +35,8 @@ int mbd_device_count(void);
  * same-type links per warp (16 samples per CTA), 6 = v2 with two interleaved 32-sample groups per 704-thread CTA.  All variants
  * produce bit-identical results; the switch exists for tests and profiling. */
 int mbd_set_kernel_variant(int v);
+/* tuning hook: slot -> link order of the one-link-per-warp mapping (slot L-1 gets the highest warp id) */
+int mbd_model_set_warp_order(mbd_model* m, const int* order, int n);
 
 /* brax.io.mjcf.load(...) result made device resident — replaces the `sys` captured by the
  * jitted env.step (/root/reference/mbd/envs/humanoidrun.py:15-17).  blob: include/mbd_model.h */

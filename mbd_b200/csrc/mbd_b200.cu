@@ -838,6 +838,13 @@ int mbd_set_kernel_variant(int v) {
   return MBD_OK;
 }
 
+// experiment hook: override the slot -> link order of the one-link-per-warp mapping (slot L-1 = highest warp id)
+int mbd_model_set_warp_order(mbd_model* m, const int* order, int n) {
+  if (!m || !order || n != m->L) return MBD_EINVAL;
+  for (int w = 0; w < n; ++w) { if (order[w] < 0 || order[w] >= n) return MBD_EINVAL; m->wl1[w][0] = m->wl1[w][1] = (signed char)order[w]; }
+  return MBD_OK;
+}
+
 int mbd_layout_info(int32_t* out, int n) {
   const int32_t v[] = {(int32_t)MBD_MODEL_MAGIC, MBD_HDR_WORDS, MBD_NFIELDS, MBD_MAXL, MBD_MAXCHILD, MBD_MAXDOF, MBD_MAXCON,
                        MBD_MAXTRACK, MBD_DOF_STRIDE, MBD_CON_STRIDE, MBD_H_DT, MBD_H_RW0, MBD_F_MASS, MBD_F_COM, MBD_F_RC,

@@ -35,7 +35,7 @@ def to_bytes(v, u):
 
 
 if "--json" in sys.argv:
-    js = {"kernel": d.get("launch__function_name", ("k_rollout", ""))[0] if False else "k_rollout_wpl<true,11,2,0>", "title": title,
+    js = {"kernel": title.split(" ")[0], "title": title,
           "dram_bytes_per_launch": to_bytes(*d['dram__bytes_read.sum']) + to_bytes(*d['dram__bytes_write.sum']),
           "duration_ms": float(d['gpu__time_duration.sum'][0]), "warp_instructions": float(d['smsp__inst_executed.sum'][0]),
           "issue_active_pct": float(d['smsp__issue_active.avg.pct_of_peak_sustained_active'][0]),
