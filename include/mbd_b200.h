@@ -37,6 +37,8 @@ int mbd_device_count(void);
 int mbd_set_kernel_variant(int v);
 /* tuning hook: slot -> link order of the one-link-per-warp mapping (slot L-1 gets the highest warp id) */
 int mbd_model_set_warp_order(mbd_model* m, const int* order, int n);
+/* tuning hook: two-group CTA warp table, map[w] = (group << 4) | slot for the 2*L warps */
+int mbd_model_set_group_map(mbd_model* m, const int* map, int n);
 
 /* brax.io.mjcf.load(...) result made device resident — replaces the `sys` captured by the
  * jitted env.step (/root/reference/mbd/envs/humanoidrun.py:15-17).  blob: include/mbd_model.h */

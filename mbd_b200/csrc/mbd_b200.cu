@@ -22,6 +22,7 @@
 #include "mbd_model.h"
 #include "xpbd_device.cuh"
 #include "xpbd_wpl.cuh"
+#include "xpbd_pk.cuh"
 
 namespace mbd {
 
@@ -97,6 +98,9 @@ struct RolloutArgs {
   // v2 mapping: link owned by (warp, half) and the half-warp offset (in units of 4 lanes) of every link's row
   signed char wl[MBD_MAXL][2];
   unsigned long long offs;
+  // multi-group CTAs: warp -> (group << 4) | link slot
+  signed char gw[32];
+  int count_x;             // group barriers: 32 * (links that are not leaves with contacts), see SyncGroup
 };
 
 template <bool FUSED, int CMAX>
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
 }
 
 // ---- v2 rollout kernel: warp per link, lane per sample (xpbd_wpl.cuh) -------------------------------------
-template <bool FUSED, int SYNC, int SPLIT, int CMAX, int GROUPS = 1>
+template <bool FUSED, int SYNC, int SPLIT, int CMAX, int GROUPS = 1, int kGroupLinks = MBD_MAXL>
 __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sblob, uint64_t* mbar_p, uint64_t* edge_bars, float* dyn) {
   stage_model_tma(sblob, mbar_p, a.blob);
   ModelSmem M;
@@ -241,8 +245,9 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
   // GROUPS independent 32-sample groups share the CTA with their warps INTERLEAVED (warp w -> group w % GROUPS,
   // link slot w / GROUPS), so the links that the mapping marks critical (highest slots) have the highest warp ids
   // of the whole CTA — the SM arbiter issues the highest eligible warp id first.
-  const int grp = (tid >> 5) % GROUPS;
-  const int l = a.wl[(tid >> 5) / GROUPS][SPLIT == 1 ? 0 : lane / kLpl];  // warp (and half) -> link
+  const int gwe = GROUPS == 1 ? (tid >> 5) : a.gw[tid >> 5];
+  const int grp = GROUPS == 1 ? 0 : (gwe >> 4);
+  const int l = a.wl[gwe & 15][SPLIT == 1 ? 0 : lane / kLpl];  // warp (and half) -> link
   const int slot = lane % kLpl;                                // sample index inside the CTA
   const int L = M.hi(MBD_H_NLINK), nu = M.hi(MBD_H_NU);
   const int HNu = a.H * nu;
@@ -288,9 +293,9 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
     s.v = V3(st[10], st[11], st[12]);
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
-  typename std::conditional<GROUPS != 1, SyncGroup,
+  typename std::conditional<GROUPS != 1, SyncGroup<kGroupLinks>,
       typename std::conditional<SYNC == 1, SyncP2P, typename std::conditional<SYNC == 2, SyncNamed, SyncCta>::type>::type>::type Y;
-  if constexpr (GROUPS != 1) { Y.id = 1 + grp; Y.count = 32 * L; }
+  if constexpr (GROUPS != 1) { Y.base = 1 + 4 * grp; Y.count_x = a.count_x; }
   if constexpr (SYNC == 2) Y.setup(M, l, L);
   if constexpr (SYNC == 1) {
     Y.pose = edge_bars; Y.terms = edge_bars + MBD_MAXL; Y.ph_pose = 0u; Y.ph_terms = 0u;
@@ -376,7 +381,204 @@ __global__ void __launch_bounds__(32 * NWARPS, MINB) k_rollout_wpl(RolloutArgs a
   __shared__ __align__(8) uint64_t mbar;
   __shared__ __align__(8) uint64_t edge_bars[2 * MBD_MAXL];
   extern __shared__ __align__(16) float dyn[];
-  rollout_wpl_body<FUSED, SYNC, SPLIT, CMAX, GROUPS>(a, sblob, &mbar, edge_bars, dyn);
+  rollout_wpl_body<FUSED, SYNC, SPLIT, CMAX, GROUPS, NWARPS / GROUPS>(a, sblob, &mbar, edge_bars, dyn);
+}
+
+// ---- packed rollout kernel: warp per link, TWO samples per lane on FFMA2 / FMUL2 / FADD2 (xpbd_pk.cuh) -----------------
+// One 64-sample group per CTA, one CTA per SM (11 warps, no register cap).  The fp32 pipe does the same work per sample
+// as the scalar kernels, but every packed instruction advances two rollouts: half the issue slots and half the
+// dependent-latency steps per sample.  Model constants are read from a duplicated (c, c) copy of the blob so that they are
+// packed operands without a repack; exchange rows are 64-bit per lane (LDS.64 / STS.64).
+template <int CMAX, class Sync>
+__device__ __forceinline__ void positional_step_pk(const pk::Model<pk::f2>& M, const pk::Cfg& c, const pk::Smem<pk::f2>& S, Sync& Y,
+                                                   pk::State<pk::f2>& s, const pk::f2 tau[MBD_MAXDOF]) {
+  pk::Carry<pk::f2, CMAX> k;
+  MBD_PH_BEGIN
+  Y.wait_pose(c.ndof > 0 ? c.parent : -1);
+  pk::phase_A<pk::f2, CMAX>(M, c, S, s, tau, k);
+  MBD_PH(0)
+  Y.arrive_terms(c.l);
+  Y.end_A(c);
+  MBD_PH(1)
+  Y.wait_terms(c.child);
+  pk::phase_B<pk::f2, CMAX>(M, c, S, s, k);
+  MBD_PH(2)
+  Y.arrive_pose(c.l);
+  Y.end_B(c);
+  MBD_PH(3)
+  Y.wait_pose(c.ndof > 0 ? c.parent : -1);
+  pk::phase_C<pk::f2, CMAX>(M, c, S, s, k);
+  MBD_PH(4)
+  Y.arrive_terms(c.l);
+  Y.end_C(c);
+  MBD_PH(5)
+  Y.wait_terms(c.child);
+  pk::phase_D<pk::f2, CMAX>(M, c, S, s, k);
+  MBD_PH(6)
+  Y.arrive_pose(c.l);
+  Y.end_D(c);
+  MBD_PH(7)
+}
+
+__device__ __forceinline__ v3 pk_lo(pk::V<pk::f2> a) { return V3(pk::lo(a.x), pk::lo(a.y), pk::lo(a.z)); }
+__device__ __forceinline__ v3 pk_hi(pk::V<pk::f2> a) { return V3(pk::hi(a.x), pk::hi(a.y), pk::hi(a.z)); }
+
+constexpr int kPkLinks = 11;       // links (= warps) per CTA the packed kernel is built for
+constexpr int kPkSamples = 64;     // samples per CTA
+constexpr size_t kPkDynBytes = (size_t)(MBD_BLOB_WORDS + kPkLinks * (pk::kXF + pk::kEF) * pk::kLanes) * sizeof(pk::f2);
+
+template <bool FUSED, int CMAX, int SYNC>
+__global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) {
+  __shared__ __align__(128) float sblob[MBD_BLOB_WORDS];
+  __shared__ __align__(8) uint64_t mbar;
+  extern __shared__ __align__(16) float dyn[];
+  stage_model_tma(sblob, &mbar, a.blob);
+  ModelSmem Ms;
+  Ms.f = sblob;
+  const int tid = threadIdx.x, lane = tid & 31, nthreads = blockDim.x;
+  pk::f2* tab = reinterpret_cast<pk::f2*>(dyn);
+  for (int i = tid; i < MBD_BLOB_WORDS; i += nthreads) tab[i] = pk::mk2(sblob[i], sblob[i]);
+  pk::Model<pk::f2> M;
+  M.t = tab;
+  M.f = sblob;
+  const int l = a.wl[tid >> 5][0];   // warp -> link (scheduler-balanced order, build_pairing)
+  const int L = M.hi(MBD_H_NLINK), nu = M.hi(MBD_H_NU);
+  const int HNu = a.H * nu;
+  const int nsub = a.nsub_override > 0 ? a.nsub_override : M.hi(MBD_H_NFRAMES);
+  const int reward_kind = M.hi(MBD_H_REWARD);
+  const int ntrack = M.hi(MBD_H_NTRACK);
+
+  if (FUSED) {
+    const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+    const int first = blockIdx.x * kPkSamples;
+    const int cnt = min(kPkSamples, a.n - first) * HNu;
+    for (int e = tid; e < cnt; e += nthreads) {
+      int ns = first + e / HNu, j = e % HNu;
+      uint32_t idx = (uint32_t)(a.n_begin + ns) * (uint32_t)HNu + (uint32_t)j;
+      a.Y0s[(size_t)ns * HNu + j] = sample_elem(a.k0, a.k1, idx, total, a.sigma, a.Ybar[j]);
+    }
+  }
+  __syncthreads();   // the duplicated table and (FUSED) this CTA's action rows are complete
+
+  pk::Smem<pk::f2> S;
+  S.X = tab + MBD_BLOB_WORDS;
+  S.E = S.X + L * pk::kXF * pk::kLanes;
+  S.lane = lane;
+  pk::Cfg c;
+  pk::load_cfg(M, l, c);
+
+  // lane holds samples 2*lane (low half) and 2*lane + 1 (high half) of the CTA
+  const int n0 = blockIdx.x * kPkSamples + 2 * lane;
+  const bool act0 = n0 < a.n, act1 = n0 + 1 < a.n;
+  const int r0 = act0 ? n0 : a.n - 1, r1 = act1 ? n0 + 1 : a.n - 1;
+
+  pk::State<pk::f2> s;
+  {
+    const float* st = a.state_init + l * MBD_STATE_STRIDE;
+    auto b = [&](int i) { return pk::mk2(st[i], st[i]); };
+    s.p = pk::mkV(b(0), b(1), b(2));
+    s.q = pk::mkQ(b(3), b(4), b(5), b(6));
+    s.w = pk::mkV(b(7), b(8), b(9));
+    s.v = pk::mkV(b(10), b(11), b(12));
+  }
+  S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
+  typename std::conditional<SYNC == 2, SyncNamed, SyncGroup<kPkLinks>>::type Y;
+  if constexpr (SYNC == 2) Y.setup(Ms, l, L);
+  else { Y.base = 1; Y.count_x = a.count_x; }
+  int my_track = -1;
+  for (int k = 0; k < ntrack; ++k)
+    if (M.hi(MBD_H_TRACK0 + k) == l) my_track = k;
+  __syncthreads();
+  if constexpr (SYNC == 2) Y.arrive_pose(l);  // the initial pose is published
+  float rsum0 = 0.0f, rsum1 = 0.0f, tacc0 = 0.0f, tacc1 = 0.0f;
+  const float* urow0 = a.Y0s + (size_t)r0 * HNu;
+  const float* urow1 = a.Y0s + (size_t)r1 * HNu;
+  for (int t = 0; t < a.H; ++t) {
+    pk::f2 tau[MBD_MAXDOF];
+#pragma unroll
+    for (int k = 0; k < MBD_MAXDOF; ++k) {
+      const int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+      const int ak = k < c.ndof ? M.li(base + MBD_D_ACT, l) : -1;
+      tau[k] = pk::mk2(0.0f, 0.0f);
+      if (ak >= 0) {
+        pk::f2 u = pk::mk2(urow0[t * nu + ak], urow1[t * nu + ak]);
+        tau[k] = pk::mul(M.l(base + MBD_D_GEAR, l), pk::clamp_(u, M.l(base + MBD_D_CLO, l), M.l(base + MBD_D_CHI, l)));
+      }
+    }
+    float rp0 = 0.0f, rp1 = 0.0f;
+    if (reward_kind == MBD_REWARD_HUMANOIDTRACK && l == 0) {
+      pk::V<pk::f2> x0 = pk::link_origin_w(M, 0, s), v0 = pk::link_origin_vel_w(M, 0, s);
+      v3 xa = pk_lo(x0), xb = pk_hi(x0), va = pk_lo(v0), vb = pk_hi(v0);
+      rp0 = 1.0f + ((-fabsf(va.x - 1.6f) - fabsf(xa.z - 1.3f)) - fabsf(xa.y) * 0.1f);
+      rp1 = 1.0f + ((-fabsf(vb.x - 1.6f) - fabsf(xb.z - 1.3f)) - fabsf(xb.y) * 0.1f);
+    }
+    for (int f = 0; f < nsub; ++f) positional_step_pk<CMAX>(M, c, S, Y, s, tau);
+    if (l == 0) {
+      float ra = rp0, rb = rp1;
+      if (reward_kind != MBD_REWARD_HUMANOIDTRACK) {
+        pk::V<pk::f2> x0 = pk::link_origin_w(M, 0, s);
+        ra = reward_post(reward_kind, pk_lo(x0));
+        rb = reward_post(reward_kind, pk_hi(x0));
+      }
+      rsum0 += ra; rsum1 += rb;
+      if (a.rewss) {
+        if (act0) a.rewss[(size_t)n0 * a.H + t] = ra;
+        if (act1) a.rewss[(size_t)(n0 + 1) * a.H + t] = rb;
+      }
+    }
+    if (my_track >= 0) {
+      pk::V<pk::f2> xx = pk::link_origin_w(M, l, s);
+      const v3 xs[2] = {pk_lo(xx), pk_hi(xx)};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const v3 x = xs[i];
+        if (a.track_pos && (i == 0 ? act0 : act1)) {
+          float* o = a.track_pos + (((size_t)(n0 + i) * a.H + t) * ntrack + my_track) * 3;
+          o[0] = x.x; o[1] = x.y; o[2] = x.z;
+        }
+        if (a.xref) {
+          int tt = t < a.href ? t : a.href - 1;
+          const float* xr = a.xref + ((size_t)my_track * a.href + tt) * 3;
+          v3 d = V3(x.x - xr[0], x.y - xr[1], x.z - xr[2]);
+          float nr = sqrtf(vdot(d, d));
+          float cl = nr < 0.5f ? nr : 0.5f;
+          float q = cl / 0.5f;
+          if (i == 0) tacc0 = fmaf(q, q, tacc0); else tacc1 = fmaf(q, q, tacc1);
+        }
+      }
+    }
+  }
+  if (l == 0) {
+    if (act0) a.rews[n0] = rsum0 / (float)a.H;
+    if (act1) a.rews[n0 + 1] = rsum1 / (float)a.H;
+  }
+  if (a.logpd && a.xref) {
+    float* Ef = reinterpret_cast<float*>(S.E);   // per-body accumulators -> shared (reuse E), summed in track order by warp 0
+    __syncthreads();
+    if (my_track >= 0) { Ef[my_track * kPkSamples + 2 * lane] = tacc0; Ef[my_track * kPkSamples + 2 * lane + 1] = tacc1; }
+    __syncthreads();
+    if (l == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float tot = 0.0f;
+        for (int k = 0; k < ntrack; ++k) tot += Ef[k * kPkSamples + 2 * lane + i];
+        if (i == 0 ? act0 : act1) a.logpd[n0 + i] = 0.0f - tot / (float)(ntrack * a.H);
+      }
+    }
+  }
+  if (a.final_state) {
+    const pk::f2 f[13] = {s.p.x, s.p.y, s.p.z, s.q.w, s.q.x, s.q.y, s.q.z, s.w.x, s.w.y, s.w.z, s.v.x, s.v.y, s.v.z};
+    if (act0) {
+      float* o = a.final_state + ((size_t)n0 * L + l) * MBD_STATE_STRIDE;
+#pragma unroll
+      for (int j = 0; j < 13; ++j) o[j] = pk::lo(f[j]);
+    }
+    if (act1) {
+      float* o = a.final_state + ((size_t)(n0 + 1) * L + l) * MBD_STATE_STRIDE;
+#pragma unroll
+      for (int j = 0; j < 13; ++j) o[j] = pk::hi(f[j]);
+    }
+  }
 }
 
 // ---- car2d (/root/reference/mbd/envs/car2d.py) ---------------------------------------------------------
@@ -742,9 +944,11 @@ struct mbd_model {
   uint32_t* blob_dev;
   int L, nu, n_frames, ntrack, max_ncon;
   // v2 kernel mappings (host side): one link per warp, and two same-type links per warp
-  signed char wl1[MBD_MAXL][2], wl2[MBD_MAXL][2];
+  signed char wl1[MBD_MAXL][2], wl2[MBD_MAXL][2], wl6[MBD_MAXL][2];
   unsigned long long offs1, offs2;
   int nwarps2;
+  signed char gw2[32];  // two-group CTA: warp -> (group << 4) | slot
+  int nlate;            // jointed leaf links with contacts (SyncGroup's late leaves)
 };
 
 // Pairs links with the same (ndof, #contacts, has-children) signature so that the two halves of a warp run
@@ -757,6 +961,9 @@ static void build_pairing(mbd_model* m, const uint32_t* blob) {
   bool used[MBD_MAXL] = {false};
   for (int l = 0; l < L; ++l) sig[l] = li(MBD_F_NDOF, l) * 64 + li(MBD_F_NCON, l) * 4 + (li(MBD_F_CHILD0, l) >= 0 ? 1 : 0);
   m->offs1 = 0; m->offs2 = 0; m->nwarps2 = 0;
+  m->nlate = 0;
+  for (int l = 0; l < L; ++l) m->nlate += (li(MBD_F_CHILD0, l) < 0 && li(MBD_F_NCON, l) > 0 && li(MBD_F_NDOF, l) > 0) ? 1 : 0;
+  for (int w = 0; w < 32; ++w) m->gw2[w] = (signed char)(((w & 1) << 4) | ((w >> 1) & 15));
   for (int l = 0; l < MBD_MAXL; ++l) { m->wl1[l][0] = (signed char)(l < L ? l : 0); m->wl1[l][1] = m->wl1[l][0]; m->wl2[l][0] = m->wl2[l][1] = 0; }
   {
     // One link per warp: warps are issued by SM sub-partition (warp id % 4).  Spread the joint work
@@ -786,6 +993,29 @@ static void build_pairing(mbd_model* m, const uint32_t* blob) {
       m->wl1[w][0] = m->wl1[w][1] = (signed char)l;
       nslot[best]++; load[best] += weight(l); conload[best] += li(MBD_F_NCON, l) > 0 ? 1.0f : 0.0f;
     }
+  }
+  {
+    // Two-group CTA (SyncGroup): the leaves with contacts are decoupled from the end-of-substep barrier, their long
+    // contact phase overlaps everybody else's torque phase — they take the LOWEST warp ids so that they do not steal
+    // issue slots from it; the links above them (the chain that waits for their terms) take the highest.
+    // Order: late leaves, root, other leaves, links that are no ancestor of a late leaf, ancestors by depth.
+    bool late[MBD_MAXL], anc[MBD_MAXL] = {false}, leaf[MBD_MAXL];
+    int depth[MBD_MAXL];
+    for (int l = 0; l < L; ++l) {
+      leaf[l] = li(MBD_F_CHILD0, l) < 0;
+      late[l] = leaf[l] && li(MBD_F_NCON, l) > 0 && li(MBD_F_NDOF, l) > 0;
+      depth[l] = 0;
+      for (int p = li(MBD_F_PARENT, l); p >= 0; p = li(MBD_F_PARENT, p)) ++depth[l];
+    }
+    for (int l = 0; l < L; ++l)
+      if (late[l]) for (int p = li(MBD_F_PARENT, l); p >= 0; p = li(MBD_F_PARENT, p)) anc[p] = true;
+    auto rank = [&](int l) { return late[l] ? 0 : (li(MBD_F_NDOF, l) == 0 ? 1 : (leaf[l] ? 2 : (!anc[l] ? 3 : 4 + depth[l]))); };
+    int order[MBD_MAXL];
+    for (int l = 0; l < L; ++l) order[l] = l;
+    for (int i = 0; i < L; ++i)
+      for (int j = i + 1; j < L; ++j)
+        if (rank(order[j]) < rank(order[i])) { int t = order[i]; order[i] = order[j]; order[j] = t; }   // stable: ties keep link order
+    for (int w = 0; w < MBD_MAXL; ++w) m->wl6[w][0] = m->wl6[w][1] = (signed char)(w < L ? order[w] : 0);
   }
   auto add_pair = [&](int a, int b) {
     int w = m->nwarps2++;
@@ -833,7 +1063,7 @@ int mbd_device_count(void) {
 }
 
 int mbd_set_kernel_variant(int v) {
-  if (v < 0 || v > 6) return MBD_EINVAL;
+  if (v < 0 || v > 9 || v == 7) return MBD_EINVAL;
   g_kernel_variant = v;
   return MBD_OK;
 }
@@ -841,7 +1071,20 @@ int mbd_set_kernel_variant(int v) {
 // experiment hook: override the slot -> link order of the one-link-per-warp mapping (slot L-1 = highest warp id)
 int mbd_model_set_warp_order(mbd_model* m, const int* order, int n) {
   if (!m || !order || n != m->L) return MBD_EINVAL;
-  for (int w = 0; w < n; ++w) { if (order[w] < 0 || order[w] >= n) return MBD_EINVAL; m->wl1[w][0] = m->wl1[w][1] = (signed char)order[w]; }
+  for (int w = 0; w < n; ++w) { if (order[w] < 0 || order[w] >= n) return MBD_EINVAL; m->wl1[w][0] = m->wl1[w][1] = m->wl6[w][0] = m->wl6[w][1] = (signed char)order[w]; }
+  return MBD_OK;
+}
+
+// experiment hook: warp -> (group, slot) table of the two-group CTA; map[w] = (group << 4) | slot
+int mbd_model_set_group_map(mbd_model* m, const int* map, int n) {
+  if (!m || !map || n != 2 * m->L || n > 32) return MBD_EINVAL;
+  int seen[2][MBD_MAXL] = {{0}};
+  for (int w = 0; w < n; ++w) {
+    int g = map[w] >> 4, sl = map[w] & 15;
+    if (g < 0 || g > 1 || sl >= m->L || seen[g][sl]) return MBD_EINVAL;
+    seen[g][sl] = 1;
+  }
+  for (int w = 0; w < n; ++w) m->gw2[w] = (signed char)map[w];
   return MBD_OK;
 }
 
@@ -919,11 +1162,37 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   // named edge barriers; two CTAs per SM (> 148 CTAs) favour plain CTA barriers (better I-cache locality)
   // beyond one 32-sample CTA per SM: two interleaved groups per 704-thread CTA (critical links get the highest warp ids)
   if (variant == 0) variant = (L == 11) ? (a.n < 2048 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 6 : 2))) : 2;
-  if (variant >= 2) {
+  // The packed kernel is built for 11-link models.  Links with two or more contacts stay on the scalar kernels: on such
+  // links the packed contact-velocity pass was observed 1 ulp away from the scalar kernels (humanoidstandup, first active
+  // thigh contact) although the same templated code matches the oracle bit for bit in the host build — open item, DESIGN.md.
+  if ((variant == 8 || variant == 9) && (L != mbd::kPkLinks || m->max_ncon > 1)) variant = 2;
+  if (variant == 8 || variant == 9) {
+    // packed kernel: 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
+    memcpy(a.wl, m->wl1, sizeof(a.wl));
+    a.count_x = 32 * (L - m->nlate);
+    const int grid = (a.n + mbd::kPkSamples - 1) / mbd::kPkSamples;
+    const int dyn = (int)mbd::kPkDynBytes;
+#define MBD_PK_ATTR(F, C, S) CK(cudaFuncSetAttribute(mbd::k_rollout_pk<F, C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn))
+#define MBD_PK_LAUNCH(C, S)                                                                     \
+  do {                                                                                          \
+    if (fused) mbd::k_rollout_pk<true, C, S><<<grid, 32 * mbd::kPkLinks, dyn, st>>>(a);         \
+    else mbd::k_rollout_pk<false, C, S><<<grid, 32 * mbd::kPkLinks, dyn, st>>>(a);              \
+  } while (0)
+    static bool pk_attr_set = false;
+    if (!pk_attr_set) {
+      MBD_PK_ATTR(true, 2, 0); MBD_PK_ATTR(false, 2, 0); MBD_PK_ATTR(true, 2, 2); MBD_PK_ATTR(false, 2, 2);
+      pk_attr_set = true;
+    }
+    if (variant == 8) MBD_PK_LAUNCH(2, 0); else MBD_PK_LAUNCH(2, 2);
+#undef MBD_PK_ATTR
+#undef MBD_PK_LAUNCH
+  } else if (variant >= 2) {
     size_t dyn = (size_t)L * (mbd::kXF + mbd::kEF) * mbd::kWplLanes * sizeof(float);
     const bool split = (variant == 5);
     memcpy(a.wl, split ? m->wl2 : m->wl1, sizeof(a.wl));
     a.offs = split ? m->offs2 : m->offs1;
+    memcpy(a.gw, m->gw2, sizeof(a.gw));
+    a.count_x = 32 * (L - m->nlate);
     if (split) {
       int grid = (a.n + 15) / 16, nw = m->nwarps2;
       if (nw <= 6) MBD_LAUNCH_WPL(6, 4, 0, 2, grid, 32 * nw);     // humanoids: 6 warps, 4 CTAs/SM
@@ -933,6 +1202,7 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
       if (L == 11 && variant == 6 && m->max_ncon <= 2) {  // two interleaved 32-sample groups per 704-thread CTA
         int grid2 = (a.n + 63) / 64;
         size_t dyn2 = 2 * dyn;
+        memcpy(a.wl, m->wl6, sizeof(a.wl));
         static bool attr_set = false;
         if (!attr_set) {
           CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));

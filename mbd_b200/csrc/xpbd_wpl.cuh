@@ -100,17 +100,45 @@ struct SyncCta {
   __device__ __forceinline__ void wait_terms(const int*) {}
   __device__ __forceinline__ void arrive_pose(int) {}
   __device__ __forceinline__ void phase_end() { __syncthreads(); }
+  template <class C> __device__ __forceinline__ void end_A(const C&) { phase_end(); }
+  template <class C> __device__ __forceinline__ void end_B(const C&) { phase_end(); }
+  template <class C> __device__ __forceinline__ void end_C(const C&) { phase_end(); }
+  template <class C> __device__ __forceinline__ void end_D(const C&) { phase_end(); }
 };
 
-// SyncGroup: a CTA that hosts G independent sample groups (warps interleaved) gives each group its own
-// hardware barrier id; semantics within a group are those of SyncCta.
+// SyncGroup: a CTA that hosts G independent sample groups gives each group its own hardware barrier ids;
+// within a group the phases are separated by group-wide barriers, except that LEAF links never hold anybody up
+// where nobody depends on them:
+//   * after A and after C a leaf only bar.arrive's (the next phase, B or D, gathers from CHILDREN: a leaf has none,
+//     so it runs straight on; its parent still sees the leaf's terms because the arrival publishes them);
+//   * after D the leaves with contacts ("late" leaves: their D phase is several times longer than anybody else's)
+//     are left out of the group barrier: everybody else syncs on id_x and then bar.arrive's on id_y, the late
+//     leaves bar.sync on id_y — they wait for their parent's pose, nobody waits for them until the end of the
+//     next A phase, which therefore overlaps the contact solve.
+// Hazards: a leaf's X row is read by nobody; its E row is read by the parent in B and D, and rewritten by the leaf
+// only in C (after the group-wide B->C barrier) and in A (after id_y, i.e. after the parent finished D).
+template <int NL>
 struct SyncGroup {
-  int id, count;
+  // ids base+0: after A and after C; base+1: after B; base+2 / base+3: after D.  A warp never touches the same id
+  // twice without a blocking group-wide barrier on ANOTHER id in between (a hardware barrier has one arrival
+  // counter: a second arrival of the same warp would be counted into the generation that is still open).
+  // bar.arrive orders the warp's earlier shared-memory writes before the barrier completes (CUTLASS NamedBarrier idiom).
+  int base, count_x;   // count_x = 32 * (links that are not late leaves)
+  static constexpr int kCount = 32 * NL;
+  static __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+  static __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+  template <class C> static __device__ __forceinline__ bool leaf(const C& c) { return c.child[0] < 0; }   // children are packed from slot 0
   __device__ __forceinline__ void wait_pose(int) {}
   __device__ __forceinline__ void arrive_terms(int) {}
   __device__ __forceinline__ void wait_terms(const int*) {}
   __device__ __forceinline__ void arrive_pose(int) {}
-  __device__ __forceinline__ void phase_end() { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+  template <class C> __device__ __forceinline__ void end_A(const C& c) { if (leaf(c)) bar_arrive(base, kCount); else bar_sync(base, kCount); }
+  template <class C> __device__ __forceinline__ void end_B(const C&) { bar_sync(base + 1, kCount); }
+  template <class C> __device__ __forceinline__ void end_C(const C& c) { end_A(c); }
+  template <class C> __device__ __forceinline__ void end_D(const C& c) {
+    if (leaf(c) && c.ncon > 0) { bar_sync(base + 3, kCount); }
+    else { bar_sync(base + 2, count_x); bar_arrive(base + 3, kCount); }
+  }
 };
 
 struct SyncP2P {
@@ -146,6 +174,10 @@ struct SyncP2P {
   }
   __device__ __forceinline__ void arrive_pose(int l) { arrive(&pose[l]); }
   __device__ __forceinline__ void phase_end() {}
+  template <class C> __device__ __forceinline__ void end_A(const C&) {}
+  template <class C> __device__ __forceinline__ void end_B(const C&) {}
+  template <class C> __device__ __forceinline__ void end_C(const C&) {}
+  template <class C> __device__ __forceinline__ void end_D(const C&) {}
 };
 
 // SyncNamed: the same edge protocol on hardware named barriers (bar.arrive / bar.sync, ids 1..15):
@@ -177,6 +209,10 @@ struct SyncNamed {
     if (my_pose_id) bar_arrive(my_pose_id, my_count);
   }
   __device__ __forceinline__ void phase_end() {}
+  template <class C> __device__ __forceinline__ void end_A(const C&) {}
+  template <class C> __device__ __forceinline__ void end_B(const C&) {}
+  template <class C> __device__ __forceinline__ void end_C(const C&) {}
+  template <class C> __device__ __forceinline__ void end_D(const C&) {}
   // returns false when the tree needs more ids than the hardware has
   __device__ __forceinline__ bool setup(const ModelSmem& M, int l, int L) {
     int nparents = 0, my_idx = -1, par_idx = -1, my_nch = 0, par_nch = 0;
@@ -249,7 +285,7 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
   }
   MBD_PH(0)
   Y.arrive_terms(c.l);
-  Y.phase_end();
+  Y.end_A(c);
   MBD_PH(1)
   // ---- B: gather reaction torques, integrator.integrate_xdd, publish pose ---------------------------
   Y.wait_terms(c.child);
@@ -268,7 +304,7 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
   MBD_PH(2)
   Y.arrive_pose(c.l);
   const v3 w_before = s.w, v_before = s.v;
-  Y.phase_end();
+  Y.end_B(c);
   MBD_PH(3)
   // ---- C: joints.position_update ---------------------------------------------------------------------
   v3 dpc = V3(0.0f, 0.0f, 0.0f);
@@ -330,7 +366,7 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
   }
   MBD_PH(4)
   Y.arrive_terms(c.l);
-  Y.phase_end();
+  Y.end_C(c);
   MBD_PH(5)
   // ---- D: gather child deltas, apply; contacts; project_xd; contact velocities; publish q,w ----------
   Y.wait_terms(c.child);
@@ -380,7 +416,7 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
   S.put_w(c.l, s.w);
   MBD_PH(6)
   Y.arrive_pose(c.l);
-  Y.phase_end();
+  Y.end_D(c);
   MBD_PH(7)
 }
 

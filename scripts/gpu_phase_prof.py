@@ -6,7 +6,8 @@ from mbd_b200 import build as b
 # instrumented build of the same sources (-DMBD_PROFILE_PHASES), kept apart from the product library
 b.OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmbd_prof.so")
 b.NVCC_FLAGS = b.NVCC_FLAGS + ["-DMBD_PROFILE_PHASES"]
-b.build(force=True)
+if not os.path.exists(b.OUT) or os.environ.get('MBD_PROF_REBUILD'):
+    b.build(force=True)
 b.is_stale = lambda: False
 import mbd_b200
 from mbd_b200 import ops, prng, _lib
@@ -17,8 +18,8 @@ m = env.device_model()
 L = _lib.lib()
 key = np.uint32([1, 2])
 names = env.sys.link_names
-for n in (32, 8192):
-    for v in (2, 3):
+for n in (8192,):
+    for v in ([int(x) for x in sys.argv[1:]] or [2, 6]):
         ops.set_kernel_variant(v)
         Y0s = torch.empty((n, 850), device="cuda:0"); rews = torch.empty(n, device="cuda:0"); Yb = torch.zeros(850, device="cuda:0")
         ops.sample_rollout(m, st, key, n, 0, n, 50, 0.88, Yb, Y0s, rews); torch.cuda.synchronize()
@@ -26,7 +27,7 @@ for n in (32, 8192):
         ops.sample_rollout(m, st, key, n, 0, n, 50, 0.88, Yb, Y0s, rews); torch.cuda.synchronize()
         out = np.zeros((16, 8), np.uint64)
         L.mbd_prof_read(out.ctypes.data_as(ctypes.c_void_p))
-        nc = (n + 31) // 32
+        nc = (n + 63) // 64 if v >= 8 else (n + 31) // 32
         per = out[:11].astype(np.float64) / (nc * 350)
         print(f"\n== n={n} variant={v} (cycles per physics step, mean over CTAs) [A, wait, B, wait, C, wait, D, wait] total")
         for l in range(11):

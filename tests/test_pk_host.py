@@ -1,0 +1,70 @@
+"""The packed-kernel physics (mbd_b200/csrc/xpbd_pk.cuh), compiled for the host, against the CPU oracle — bit for bit.
+
+The sm_100a kernel k_rollout_pk instantiates the same templated phase functions with T = f2 (two samples per thread on
+FFMA2/FMUL2/FADD2).  Here they are built with g++ for T = float and for the {float, float} emulation of f2 and driven link
+by link, phase by phase (tests/host_pk/pk_harness.cpp).  What this pins without a GPU: the translation of every physics
+expression into the scalar layer, the phase split, the two-sample data flow."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import mbd_b200
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("pk") / "libpk_host.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "mbd_b200", "csrc"), os.path.join(ROOT, "tests", "host_pk", "pk_harness.cpp"), "-o", so],
+                   check=True, env={**os.environ, "CC": "", "CXX": ""})
+    return ctypes.CDLL(so)
+
+
+def _run(lib, blob, state, Y0s, packed, nsub=0):
+    blob = np.ascontiguousarray(blob, dtype=np.uint32)
+    L = int(blob.view(np.int32)[1])
+    state = np.ascontiguousarray(state, dtype=np.float32).reshape(L, 13)
+    Y0s = np.ascontiguousarray(Y0s, dtype=np.float32)
+    n, H, _ = Y0s.shape
+    rews = np.zeros(n, np.float32)
+    final = np.zeros((n, L, 13), np.float32)
+    rc = lib.pk_host_rollout(blob.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), state.ctypes.data_as(_f32p), Y0s.ctypes.data_as(_f32p),
+                             n, H, packed, nsub, rews.ctypes.data_as(_f32p), final.ctypes.data_as(_f32p))
+    assert rc == 0
+    return rews, final
+
+
+def _case(env_name, n, H, seed, scale=0.88):
+    env = mbd_b200.envs.get_env(env_name)
+    rng = np.random.default_rng(seed)
+    state = env.reset(mbd_b200.prng.PRNGKey(seed)).pipeline_state.raw
+    Y0s = np.clip(rng.normal(size=(n, H, env.action_size)) * scale, -1, 1).astype(np.float32)
+    return env, state, Y0s
+
+
+@pytest.mark.parametrize("env_name,n,H", [("humanoidrun", 7, 12), ("humanoidstandup", 5, 8), ("humanoidtrack", 4, 10)])
+@pytest.mark.parametrize("packed", [0, 1], ids=["float", "f2"])
+def test_phases_match_oracle_bit_exact(harness, env_name, n, H, packed):
+    env, state, Y0s = _case(env_name, n, H, seed=3)
+    ref = orc.xpbd_rollout(env.blob, state, Y0s, want_final=True)
+    rews, final = _run(harness, env.blob, state, Y0s, packed)
+    assert np.array_equal(final.view(np.uint32), ref["final"].view(np.uint32))
+    if env_name != "humanoidtrack":  # its reward is taken before the step; the harness only implements post-step rewards
+        assert np.array_equal(rews.view(np.uint32), ref["rews"].view(np.uint32))
+
+
+def test_two_sample_type_with_contacts_and_saturated_actions(harness):
+    env, state, Y0s = _case("humanoidrun", 6, 40, seed=11, scale=3.0)   # long enough for falls and foot contacts
+    Y0s[1] = 0.0
+    ref = orc.xpbd_rollout(env.blob, state, Y0s, want_final=True)
+    for packed in (0, 1):
+        rews, final = _run(harness, env.blob, state, Y0s, packed)
+        assert np.array_equal(final.view(np.uint32), ref["final"].view(np.uint32))
+        assert np.array_equal(rews.view(np.uint32), ref["rews"].view(np.uint32))
