@@ -1162,10 +1162,7 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   // named edge barriers; two CTAs per SM (> 148 CTAs) favour plain CTA barriers (better I-cache locality)
   // beyond one 32-sample CTA per SM: two interleaved groups per 704-thread CTA (critical links get the highest warp ids)
   if (variant == 0) variant = (L == 11) ? (a.n < 2048 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 6 : 2))) : 2;
-  // The packed kernel is built for 11-link models.  Links with two or more contacts stay on the scalar kernels: on such
-  // links the packed contact-velocity pass was observed 1 ulp away from the scalar kernels (humanoidstandup, first active
-  // thigh contact) although the same templated code matches the oracle bit for bit in the host build — open item, DESIGN.md.
-  if ((variant == 8 || variant == 9) && (L != mbd::kPkLinks || m->max_ncon > 1)) variant = 2;
+  if ((variant == 8 || variant == 9) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
   if (variant == 8 || variant == 9) {
     // packed kernel: 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
     memcpy(a.wl, m->wl1, sizeof(a.wl));
@@ -1181,9 +1178,11 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
     static bool pk_attr_set = false;
     if (!pk_attr_set) {
       MBD_PK_ATTR(true, 2, 0); MBD_PK_ATTR(false, 2, 0); MBD_PK_ATTR(true, 2, 2); MBD_PK_ATTR(false, 2, 2);
+      MBD_PK_ATTR(true, MBD_MAXCON, 0); MBD_PK_ATTR(false, MBD_MAXCON, 0); MBD_PK_ATTR(true, MBD_MAXCON, 2); MBD_PK_ATTR(false, MBD_MAXCON, 2);
       pk_attr_set = true;
     }
-    if (variant == 8) MBD_PK_LAUNCH(2, 0); else MBD_PK_LAUNCH(2, 2);
+    if (m->max_ncon <= 2) { if (variant == 8) MBD_PK_LAUNCH(2, 0); else MBD_PK_LAUNCH(2, 2); }
+    else { if (variant == 8) MBD_PK_LAUNCH(MBD_MAXCON, 0); else MBD_PK_LAUNCH(MBD_MAXCON, 2); }
 #undef MBD_PK_ATTR
 #undef MBD_PK_LAUNCH
   } else if (variant >= 2) {

@@ -34,8 +34,8 @@ namespace pk {
 #if PK_DEVICE
 struct f2 { unsigned long long v; };
 PK_FN f2 mk2(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
-PK_FN float lo(f2 x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return a; }
-PK_FN float hi(f2 x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return b; }
+PK_FN float lo(f2 x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); (void)b; return a; }
+PK_FN float hi(f2 x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); (void)a; return b; }
 PK_FN f2 mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 PK_FN f2 add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 PK_FN f2 sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
@@ -49,6 +49,30 @@ PK_FN f2 mul(f2 a, f2 b) { return mk2(a.a * b.a, a.b * b.b); }
 PK_FN f2 add(f2 a, f2 b) { return mk2(a.a + b.a, a.b + b.b); }
 PK_FN f2 sub(f2 a, f2 b) { return mk2(a.a - b.a, a.b - b.b); }
 PK_FN f2 fma(f2 a, f2 b, f2 c) { return mk2(fmaf(a.a, b.a, c.a), fmaf(a.b, b.b, c.b)); }
+#endif
+// ptxas 12.9 CONTRACTS a packed multiply whose only use is a packed add/sub into FFMA2 — even with the explicit .rn
+// qualifiers, with -fmad=false on nvcc and on ptxas, across an opaque asm barrier, and when the product is written
+// fma(a, b, -0) (checked on sm_100a; the scalar mul.rn.f32 + add.rn.f32 pair is never fused).  That silently changes
+// rounding wherever the arithmetic contract has a separate multiply and add.  add_nf / sub_nf ("no fuse") do the
+// addition on the two halves with scalar FADDs, which ptxas leaves alone; they are used wherever an operand of an
+// add/sub is (or may be, through copies and selects) a packed product.  tests/test_pk_host.py::test_no_packed_contraction
+// compares the packed instruction counts of the PTX and of the SASS of the physics.
+#if PK_DEVICE
+PK_FN f2 add_nf(f2 a, f2 b) {
+  float r0, r1;
+  asm("add.rn.f32 %0, %1, %2;" : "=f"(r0) : "f"(lo(a)), "f"(lo(b)));
+  asm("add.rn.f32 %0, %1, %2;" : "=f"(r1) : "f"(hi(a)), "f"(hi(b)));
+  return mk2(r0, r1);
+}
+PK_FN f2 sub_nf(f2 a, f2 b) {
+  float r0, r1;
+  asm("sub.rn.f32 %0, %1, %2;" : "=f"(r0) : "f"(lo(a)), "f"(lo(b)));
+  asm("sub.rn.f32 %0, %1, %2;" : "=f"(r1) : "f"(hi(a)), "f"(hi(b)));
+  return mk2(r0, r1);
+}
+#else
+PK_FN f2 add_nf(f2 a, f2 b) { return add(a, b); }
+PK_FN f2 sub_nf(f2 a, f2 b) { return sub(a, b); }
 #endif
 // unpack / negate / repack: ptxas folds it into the operand's negate modifier of FFMA2 / FADD2 / FMUL2
 PK_FN f2 neg(f2 a) { return mk2(-lo(a), -hi(a)); }
@@ -68,6 +92,8 @@ PK_FN float mul(float a, float b) { return a * b; }
 PK_FN float add(float a, float b) { return a + b; }
 PK_FN float sub(float a, float b) { return a - b; }
 PK_FN float fma(float a, float b, float c) { return fmaf(a, b, c); }
+PK_FN float add_nf(float a, float b) { return a + b; }
+PK_FN float sub_nf(float a, float b) { return a - b; }
 PK_FN float neg(float a) { return -a; }
 PK_FN float abs_(float a) { return fabsf(a); }
 PK_FN bool lt(float x, float y) { return x < y; }
@@ -151,8 +177,8 @@ PK_FN T atan2_(T y, T x) {
   p = fma(p, z, bc<T>(-3.333306611e-01f));
   p = fma(p, z, bc<T>(1.0f));
   T r = mul(t, p);
-  r = sel(gt(ay, ax), sub(bc<T>(MBD_HALF_PI_F), r), r);
-  r = sel(lt(x, zero), sub(bc<T>(MBD_PI_F), r), r);
+  r = sel(gt(ay, ax), sub_nf(bc<T>(MBD_HALF_PI_F), r), r);   // r is a product here
+  r = sel(lt(x, zero), sub_nf(bc<T>(MBD_PI_F), r), r);
   r = sel(lt(y, zero), neg(r), r);
   return r;
 }

@@ -76,6 +76,10 @@ template <class T> PK_FN Q<T> qnormalize(Q<T> q) {
   return mkQ(mul(q.w, inv), mul(q.x, inv), mul(q.y, inv), mul(q.z, inv));
 }
 template <class T> PK_FN Q<T> qadd(Q<T> a, Q<T> b) { return mkQ(add(a.w, b.w), add(a.x, b.x), add(a.y, b.y), add(a.z, b.z)); }
+// the same sums for operands that are (or may be) packed products: see add_nf in pk_scalar.cuh
+template <class T> PK_FN V<T> vadd_nf(V<T> a, V<T> b) { return mkV(add_nf(a.x, b.x), add_nf(a.y, b.y), add_nf(a.z, b.z)); }
+template <class T> PK_FN V<T> vsub_nf(V<T> a, V<T> b) { return mkV(sub_nf(a.x, b.x), sub_nf(a.y, b.y), sub_nf(a.z, b.z)); }
+template <class T> PK_FN Q<T> qadd_nf(Q<T> a, Q<T> b) { return mkQ(add_nf(a.w, b.w), add_nf(a.x, b.x), add_nf(a.y, b.y), add_nf(a.z, b.z)); }
 template <class T> PK_FN Q<T> qscale(Q<T> a, T s) { return mkQ(mul(a.w, s), mul(a.x, s), mul(a.y, s), mul(a.z, s)); }
 
 // ---- model table: T-typed copy of the blob's float fields (f2: every word duplicated), ints from the blob -------------
@@ -138,7 +142,7 @@ template <class T> PK_FN void axis_angle_1dof(Q<T> j, T& psi, T& r10, T& r20) {
   const T one = bc<T>(1.0f), two = bc<T>(2.0f);
   T w = j.w, x = j.x, y = j.y, z = j.z;
   T r12 = mul(two, fma(y, z, neg(mul(w, x))));
-  T r22 = sub(one, mul(two, fma(y, y, mul(x, x))));
+  T r22 = sub_nf(one, mul(two, fma(y, y, mul(x, x))));
   r10 = mul(two, fma(x, y, mul(w, z)));
   r20 = mul(two, fma(x, z, neg(mul(w, y))));
   psi = atan2_(neg(r12), r22);
@@ -146,11 +150,11 @@ template <class T> PK_FN void axis_angle_1dof(Q<T> j, T& psi, T& r10, T& r20) {
 template <class T> PK_FN void axis_angle_ang(Q<T> j, T parity, Angles<T>& o) {
   const T zero = bc<T>(0.0f), one = bc<T>(1.0f), two = bc<T>(2.0f);
   T w = j.w, x = j.x, y = j.y, z = j.z;
-  T r00 = sub(one, mul(two, fma(z, z, mul(y, y))));
+  T r00 = sub_nf(one, mul(two, fma(z, z, mul(y, y))));
   T r01 = mul(two, fma(x, y, neg(mul(w, z))));
   T r02 = mul(two, fma(x, z, mul(w, y)));
   T r12 = mul(two, fma(y, z, neg(mul(w, x))));
-  T r22 = sub(one, mul(two, fma(y, y, mul(x, x))));
+  T r22 = sub_nf(one, mul(two, fma(y, y, mul(x, x))));
   o.r10 = mul(two, fma(x, y, mul(w, z)));
   o.r20 = mul(two, fma(x, z, neg(mul(w, y))));
   T psi = atan2_(neg(r12), r22);
@@ -174,12 +178,12 @@ PK_FN void contact_position_plane(const Model<T>& M, int l, int ci, T im, V<T> p
   const T radius = M.l(base + 3, l), mu = M.l(base + 4, l);
   V<T> centre = vadd(p, vrotate(M.l3(base, l), q));
   T dist = sub(centre.z, radius);
-  V<T> cp = mkV(centre.x, centre.y, sub(centre.z, add(radius, mul(bc<T>(0.5f), dist))));
+  V<T> cp = mkV(centre.x, centre.y, sub(centre.z, add_nf(radius, mul(bc<T>(0.5f), dist))));
   auto coll = lt(dist, zero);
   V<T> r = vsub(cp, p);
   T w = add(im, fma(r.x, r.x, mul(r.y, r.y)));
   T dl = sel(coll, div_(neg(dist), add(w, bc<T>(1e-6f))), zero);
-  dp.z = add(dp.z, mul(dl, im));
+  dp.z = add_nf(dp.z, mul(dl, im));
   dq = qadd(dq, vqmul_xy(mul(r.y, dl), neg(mul(r.x, dl)), q));
   V<T> rl = vinv_rotate(r, q);
   V<T> pbar = vadd(p_prev, vrotate(rl, q_prev));
@@ -193,8 +197,8 @@ PK_FN void contact_position_plane(const Model<T>& M, int l, int ci, T im, V<T> p
   auto stat = mand(coll, lt(abs_(dlt), mul(mu, abs_(dl))));
   T m = sel(stat, dlt, zero);
   T ptx = mul(ntx, m), pty = mul(nty, m);
-  dp.x = add(dp.x, mul(ptx, im));
-  dp.y = add(dp.y, mul(pty, im));
+  dp.x = add_nf(dp.x, mul(ptx, im));
+  dp.y = add_nf(dp.y, mul(pty, im));
   dq = qadd(dq, vqmul(mkV(neg(mul(r.z, pty)), mul(r.z, ptx), fma(r.x, pty, neg(mul(r.y, ptx)))), q));
   dl_out = dl;
   cp_out = cp;
@@ -206,7 +210,7 @@ PK_FN void contact_velocity_plane(const Model<T>& M, int l, int ci, T im, T inv_
   const T zero = bc<T>(0.0f);
   const T mu = M.l(MBD_F_CON0 + ci * MBD_CON_STRIDE + 4, l);
   V<T> r = vsub(cp, p);
-  V<T> rel = vadd(v, vcross(w, r));
+  V<T> rel = vadd_nf(v, vcross(w, r));   // v is a product (project_xd)
   T vn = rel.z;
   T vtn = sqrt_(fma(rel.y, rel.y, mul(rel.x, rel.x)));
   T inv = sel(eq(vtn, zero), zero, rcp_(vtn));
@@ -222,10 +226,10 @@ PK_FN void contact_velocity_plane(const Model<T>& M, int l, int ci, T im, T inv_
   T rest = mul(neg(elasticity), vn_old);
   rest = sel(lt(rest, zero), rest, zero);
   T wn = add(im, fma(r.x, r.x, mul(r.y, r.y)));
-  T prz = mul(add(neg(vn), rest), rcp_(add(wn, bc<T>(1e-6f))));
+  T prz = mul(add_nf(neg(vn), rest), rcp_(add(wn, bc<T>(1e-6f))));   // rest may be a product
   auto live = eq(dl, zero);   // dl == 0: no impulse at all
   V<T> P = mkV(sel(live, zero, pdx), sel(live, zero, pdy), sel(live, zero, sel(le(vn_old, zero), prz, zero)));
-  dv = vadd(dv, vscale(P, im));
+  dv = vadd_nf(dv, vscale(P, im));
   dw = vadd(dw, vcross(r, P));
 }
 
@@ -243,7 +247,7 @@ PK_FN void phase_A(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
     Q<T> a_p = qmul(qp, M.l4(MBD_F_PQ, c.l));
     Q<T> a_c = qmul(s.q, M.l4(MBD_F_JQ, c.l));
     Q<T> j = qmul(qconj(a_p), a_c);
-    V<T> jd = vinv_rotate(vsub(s.w, wp), a_p);
+    V<T> jd = vinv_rotate(vsub_nf(s.w, wp), a_p);   // s.w is a product after project_xd
     V<T> tq = vscale(jd, neg(M.l(MBD_F_ANG_DAMP, c.l)));
     if (c.ndof == 1) {
       T psi, r10, r20;
@@ -283,7 +287,7 @@ PK_FN void phase_B(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
   const T dt = M.h(MBD_H_DT), ad = M.h(MBD_H_ANG_DAMP), vd = M.h(MBD_H_VEL_DAMP);
   s.w = mkV(fma(acc.x, dt, mul(s.w.x, ad)), fma(acc.y, dt, mul(s.w.y, ad)), fma(acc.z, dt, mul(s.w.z, ad)));
   s.v = mkV(fma(M.h(MBD_H_GX), dt, mul(s.v.x, vd)), fma(M.h(MBD_H_GY), dt, mul(s.v.y, vd)), fma(M.h(MBD_H_GZ), dt, mul(s.v.z, vd)));
-  s.q = qnormalize(qadd(s.q, vqmul(vscale(s.w, M.h(MBD_H_HALF_DT)), s.q)));
+  s.q = qnormalize(qadd_nf(s.q, vqmul(vscale(s.w, M.h(MBD_H_HALF_DT)), s.q)));   // s.q is a product (qnormalize)
   s.p = vfma(s.v, dt, s.p);
   S.put_p(c.l, s.p);
   S.put_q(c.l, s.q);
@@ -331,7 +335,7 @@ PK_FN void phase_C(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
       axis_angle_ang(j, M.l(MBD_F_PARITY, c.l), ja);
       T e0 = sub(ja.ang[0], clamp_(ja.ang[0], M.l(b0 + MBD_D_LO, c.l), M.l(b0 + MBD_D_HI, c.l)));
       T e1 = sub(ja.ang[1], clamp_(ja.ang[1], M.l(b1 + MBD_D_LO, c.l), M.l(b1 + MBD_D_HI, c.l)));
-      T e2 = sub(ja.ang[2], clamp_(ja.ang[2], M.l(b2 + MBD_D_LO, c.l), M.l(b2 + MBD_D_HI, c.l)));
+      T e2 = sub_nf(ja.ang[2], clamp_(ja.ang[2], M.l(b2 + MBD_D_LO, c.l), M.l(b2 + MBD_D_HI, c.l)));
       dqj = vscale(ja.ax[0], e0);
       dqj = vfma(ja.ax[1], e1, dqj);
       dqj = vfma(ja.ax[2], e2, dqj);
@@ -348,9 +352,9 @@ PK_FN void phase_C(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
     const T sp = M.h(MBD_H_SCALE_POS);
     const T hsp = mul(bc<T>(0.5f), sp), hsa = mul(bc<T>(0.5f), M.h(MBD_H_SCALE_ANG));
     k.dpc = vscale(dp_c, sp);
-    k.dqc = qadd(qscale(dq_c, hsp), qscale(dqa_c, hsa));
+    k.dqc = qadd_nf(qscale(dq_c, hsp), qscale(dqa_c, hsa));
     S.put_e3(c.l, 0, vscale(dp_p, sp));
-    S.put_e4(c.l, 3, qadd(qscale(dq_p, mul(neg(hsp), ii_p)), qscale(dqa_p, mul(neg(hsa), ii_p))));
+    S.put_e4(c.l, 3, qadd_nf(qscale(dq_p, mul(neg(hsp), ii_p)), qscale(dqa_p, mul(neg(hsa), ii_p))));
   }
 }
 
@@ -365,10 +369,10 @@ PK_FN void phase_D(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
 #pragma unroll
 #endif
     for (int i = 0; i < MBD_MAXCHILD; ++i) {
-      if (c.child[i] >= 0) { dp = vadd(dp, S.e3(c.child[i], 0)); dq = qadd(dq, S.e4(c.child[i], 3)); }
+      if (c.child[i] >= 0) { dp = vadd_nf(dp, S.e3(c.child[i], 0)); dq = qadd(dq, S.e4(c.child[i], 3)); }   // dp starts as a product
     }
-    s.p = vadd(s.p, dp);
-    s.q = qnormalize(qadd(s.q, dq));
+    s.p = vadd_nf(s.p, dp);
+    s.q = qnormalize(qadd_nf(s.q, dq));
   }
   T dlam[CMAX];
   V<T> cpos[CMAX];
@@ -386,7 +390,7 @@ PK_FN void phase_D(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
     }
     const T cs = M.h(MBD_H_COLLIDE_SCALE);
     s.p = vfma(dp, cs, s.p);
-    s.q = qnormalize(qadd(s.q, qscale(dq, mul(bc<T>(0.5f), cs))));
+    s.q = qnormalize(qadd_nf(s.q, qscale(dq, mul(bc<T>(0.5f), cs))));
   }
   {
     s.v = vscale(vsub(s.p, k.p_prev), M.h(MBD_H_INV_DT));
@@ -405,8 +409,8 @@ PK_FN void phase_D(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
       if (ci < c.ncon)
         contact_velocity_plane(M, c.l, ci, M.l(MBD_F_INV_MASS, c.l), M.h(MBD_H_INV_DT), M.h(MBD_H_ELASTICITY), s.p, v0, w0, k.v_before,
                                k.w_before, cpos[ci], dlam[ci], dv, dw);
-    s.v = vadd(s.v, dv);
-    s.w = vadd(s.w, dw);
+    s.v = vadd_nf(s.v, dv);   // s.v, s.w are products (project_xd)
+    s.w = vadd_nf(s.w, dw);
   }
   S.put_q(c.l, s.q);
   S.put_w(c.l, s.w);

@@ -68,3 +68,27 @@ def test_two_sample_type_with_contacts_and_saturated_actions(harness):
         rews, final = _run(harness, env.blob, state, Y0s, packed)
         assert np.array_equal(final.view(np.uint32), ref["final"].view(np.uint32))
         assert np.array_equal(rews.view(np.uint32), ref["rews"].view(np.uint32))
+
+
+def test_no_packed_contraction(tmp_path):
+    """ptxas fuses a packed multiply that feeds a packed add/sub into FFMA2 even under .rn and -fmad=false, which would
+    change rounding where the arithmetic contract has a separate multiply and add.  The physics routes every such sum
+    through add_nf / sub_nf (pk_scalar.cuh); here the packed multiplies of the PTX must all survive into the SASS."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not (os.path.exists(nvcc) and os.path.exists(cuobjdump)):
+        pytest.skip("CUDA toolkit not available")
+    src = os.path.join(ROOT, "tests", "host_pk", "pk_device_probe.cu")
+    flags = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false", "-I" + os.path.join(ROOT, "include"),
+             "-I" + os.path.join(ROOT, "mbd_b200", "csrc")]
+    ptx, cubin = str(tmp_path / "probe.ptx"), str(tmp_path / "probe.cubin")
+    subprocess.run([nvcc] + flags + ["-ptx", src, "-o", ptx], check=True, capture_output=True)
+    subprocess.run([nvcc] + flags + ["-cubin", src, "-o", cubin], check=True, capture_output=True)
+    text = open(ptx).read()
+    n_mul = text.count("mul.rn.f32x2")
+    n_fma = text.count("fma.rn.f32x2")
+    sass = subprocess.run([cuobjdump, "-sass", cubin], check=True, capture_output=True, text=True).stdout
+    assert n_mul > 500 and n_fma > 500
+    assert sass.count("FMUL2") == n_mul, f"{n_mul - sass.count('FMUL2')} packed products were contracted into FFMA2"
+    assert sass.count("FFMA2") <= n_fma
