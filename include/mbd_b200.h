@@ -32,8 +32,10 @@ const char* mbd_last_error(void);
 int mbd_device_count(void);
 /* rollout kernel mapping: 0 = auto (by shard size), 1 = v1 (one link per lane), 2/3/4 = v2 (one link per
  * warp, lane = sample) with CTA-wide / named-barrier / mbarrier phase synchronisation, 5 = v2 with two
- * same-type links per warp (16 samples per CTA), 6 = v2 with two interleaved 32-sample groups per 704-thread CTA.  All variants
- * produce bit-identical results; the switch exists for tests and profiling. */
+ * same-type links per warp (16 samples per CTA), 6 = v2 with two interleaved 32-sample groups per 704-thread CTA
+ * (leaf links decoupled from the group barriers), 8/9 = packed kernel: two samples per lane on FFMA2/FMUL2/FADD2,
+ * 64 samples per CTA, group barriers / named edge barriers (11-link models; others fall back to 2).  7 is unused.
+ * All variants produce bit-identical results; the switch exists for tests and profiling. */
 int mbd_set_kernel_variant(int v);
 /* tuning hook: slot -> link order of the one-link-per-warp mapping (slot L-1 gets the highest warp id) */
 int mbd_model_set_warp_order(mbd_model* m, const int* order, int n);
