@@ -9,6 +9,37 @@
 #include <string.h>
 #include <vector>
 
+#include "pk_scalar.cuh"
+
+// ---- a third scalar type: one sample, every operation counted (algorithmic flops "counted by instrumenting
+// the CPU restatement").  Lives in mbd::pk so that the templated physics finds the overloads by ADL. ------------------
+namespace mbd {
+namespace pk {
+struct OpCount { unsigned long long mul, add, fma, div, rcp, sqrt, cmp, sel, neg; };
+static OpCount g_ops;
+struct c1 { float v; };
+static inline c1 mkc(float v) { c1 r; r.v = v; return r; }
+static inline c1 mul(c1 a, c1 b) { ++g_ops.mul; return mkc(a.v * b.v); }
+static inline c1 add(c1 a, c1 b) { ++g_ops.add; return mkc(a.v + b.v); }
+static inline c1 sub(c1 a, c1 b) { ++g_ops.add; return mkc(a.v - b.v); }
+static inline c1 add_nf(c1 a, c1 b) { return add(a, b); }
+static inline c1 sub_nf(c1 a, c1 b) { return sub(a, b); }
+static inline c1 fma(c1 a, c1 b, c1 c) { ++g_ops.fma; return mkc(fmaf(a.v, b.v, c.v)); }
+static inline c1 neg(c1 a) { ++g_ops.neg; return mkc(-a.v); }
+static inline c1 abs_(c1 a) { ++g_ops.neg; return mkc(fabsf(a.v)); }
+static inline bool lt(c1 x, c1 y) { ++g_ops.cmp; return x.v < y.v; }
+static inline bool le(c1 x, c1 y) { ++g_ops.cmp; return x.v <= y.v; }
+static inline bool gt(c1 x, c1 y) { ++g_ops.cmp; return x.v > y.v; }
+static inline bool ge(c1 x, c1 y) { ++g_ops.cmp; return x.v >= y.v; }
+static inline bool eq(c1 x, c1 y) { ++g_ops.cmp; return x.v == y.v; }
+static inline c1 sel(bool m, c1 x, c1 y) { ++g_ops.sel; return m ? x : y; }
+static inline c1 div_(c1 a, c1 b) { ++g_ops.div; return mkc(a.v / b.v); }
+static inline c1 rcp_(c1 x) { ++g_ops.rcp; return mkc(1.0f / x.v); }
+static inline c1 sqrt_(c1 x) { ++g_ops.sqrt; return mkc(sqrtf(x.v)); }
+template <> struct Bc<c1> { static c1 of(float c) { return mkc(c); } };
+}  // namespace pk
+}  // namespace mbd
+
 #include "xpbd_pk.cuh"
 
 using namespace mbd::pk;
@@ -28,6 +59,11 @@ template <> struct Lanes<float> {
   static constexpr int N = 1;
   static float make(const float* v) { return v[0]; }
   static float get(float x, int) { return x; }
+};
+template <> struct Lanes<c1> {
+  static constexpr int N = 1;
+  static c1 make(const float* v) { return mkc(v[0]); }
+  static float get(c1 x, int) { return x.v; }
 };
 template <> struct Lanes<f2> {
   static constexpr int N = 2;
@@ -95,6 +131,17 @@ static void rollout(const uint32_t* blob, const float* state_init, const float* 
         }
     }
   }
+}
+
+// Operation counts of ONE rollout (n = 1): ops[9] = mul, add/sub, fma, div, rcp, sqrt, compare, select, neg/abs —
+// physics only (the phases; reward and action clipping excluded by resetting around them would be overkill: they are < 0.1 %).
+extern "C" int pk_host_count_ops(const uint32_t* blob, const float* state_init, const float* Y0s, int H, int nsub_override,
+                                 unsigned long long* ops, float* rews) {
+  memset(&g_ops, 0, sizeof(g_ops));
+  rollout<c1, MBD_MAXCON>(blob, state_init, Y0s, 1, H, nsub_override, rews, nullptr);
+  const unsigned long long v[9] = {g_ops.mul, g_ops.add, g_ops.fma, g_ops.div, g_ops.rcp, g_ops.sqrt, g_ops.cmp, g_ops.sel, g_ops.neg};
+  memcpy(ops, v, sizeof(v));
+  return 0;
 }
 
 extern "C" int pk_host_rollout(const uint32_t* blob, const float* state_init, const float* Y0s, int n, int H, int packed, int nsub_override,

@@ -92,3 +92,22 @@ def test_no_packed_contraction(tmp_path):
     assert n_mul > 500 and n_fma > 500
     assert sass.count("FMUL2") == n_mul, f"{n_mul - sass.count('FMUL2')} packed products were contracted into FFMA2"
     assert sass.count("FFMA2") <= n_fma
+
+
+def test_algorithmic_operation_count(harness):
+    """the flops of one XPBD substep, counted by running the physics with an operation-counting scalar type
+    (DESIGN.md section 4 quotes these numbers; the SASS-level count of the kernel is ~15 % higher because division,
+    reciprocal and square root expand into a MUFU seed plus Newton FMAs on the device)."""
+    env, state, Y0s = _case("humanoidrun", 1, 50, seed=1)
+    blob = np.ascontiguousarray(env.blob, dtype=np.uint32)
+    st = np.ascontiguousarray(state, dtype=np.float32).reshape(11, 13)
+    ops = (ctypes.c_ulonglong * 9)()
+    rews = np.zeros(1, np.float32)
+    harness.pk_host_count_ops(blob.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), st.ctypes.data_as(_f32p), Y0s.ctypes.data_as(_f32p),
+                              50, 0, ops, rews.ctypes.data_as(_f32p))
+    ref = orc.xpbd_rollout(env.blob, state, Y0s)
+    assert rews[0] == ref["rews"][0]                      # the counting type computes the same rollout
+    mul, add, fma, div, rcp, sqrt = [ops[i] / (50 * 7) for i in range(6)]
+    flop = mul + add + 2 * fma + div + rcp + sqrt
+    assert 9000 < flop < 9700                             # 9.34 kFLOP per sample and substep (2296 mul, 799 add, 3024 fma)
+    assert 190 <= div + rcp + sqrt <= 200                 # 64 div + 62 rcp + 68 sqrt: the contact-free part is data independent
