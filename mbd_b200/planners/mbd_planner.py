@@ -114,7 +114,11 @@ def run_diffusion(args: Args, log_every: int = 10, return_trajectory: bool = Fal
         np.save(f"{path}/mu_0ts.npy", Yi.cpu().numpy())
         if args.env_name == "car2d":
             _render_car2d(env, state_init, Yi[-1].cpu().numpy(), args, path)
-        # HTML rendering of Brax systems (brax.io.html) is out of scope (SURVEY C2 render_us)
+        elif env.kind == "xpbd":
+            # the reference writes rollout.html through brax.io.html (mbd_planner.py:168-178); Brax is not a dependency
+            # here, so the same trajectory (world pose of every link per env step) is written as arrays instead
+            from ..utils import render_us
+            np.savez(f"{path}/rollout_states.npz", **render_us(env.step, env.sys, state_init, Yi[-1].cpu().numpy()))
     rew_final = final_reward(env, engine, Yi[-1])
     if return_trajectory:
         return rew_final, Yi

@@ -53,3 +53,26 @@ def eval_us(step_env, state, us):
                           want_rewss=True)
         return out["rewss"][0].cpu().numpy()
     return rollout_us(step_env, state, us)[0]
+
+
+def trajectory_arrays(env, pipeline_states):
+    """The per-step world poses the reference hands to `brax.io.html.render` (utils.py:23-34 `render_us`,
+    scripts/vis_diffusion.py:115-143): x.pos [T,L,3], x.rot [T,L,4] (w,x,y,z), plus q [T,nq], qd [T,nv]."""
+    pos = np.stack([np.asarray(ps.x.pos, dtype=np.float32) for ps in pipeline_states])
+    rot = np.stack([np.asarray(ps.x.rot, dtype=np.float32) for ps in pipeline_states])
+    q = np.stack([np.asarray(ps.q, dtype=np.float32) for ps in pipeline_states])
+    qd = np.stack([np.asarray(ps.qd, dtype=np.float32) for ps in pipeline_states])
+    return dict(pos=pos, rot=rot, q=q, qd=qd, dt=np.float32(env.dt), link_names=np.asarray(list(env.sys.link_names)))
+
+
+def render_us(step_env, sys, state, us):
+    """Mirror of mbd.utils.render_us: steps `us` from `state` and returns the trajectory (initial state first, as the
+    reference's `rollout` list).  The reference turns that list into a Brax HTML page; Brax is not a dependency here,
+    so the trajectory itself is returned (see `trajectory_arrays`, written to results/<env>/rollout_states.npz by the CLI)."""
+    env = _env_of(step_env)
+    us = np.asarray(us.detach().cpu().numpy() if isinstance(us, torch.Tensor) else us, dtype=np.float32)
+    rollout = []
+    for i in range(us.shape[0]):
+        rollout.append(state.pipeline_state)
+        state = step_env(state, us[i])
+    return trajectory_arrays(env, rollout) if env is not None and getattr(env, "kind", None) == "xpbd" else rollout
