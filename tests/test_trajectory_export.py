@@ -28,8 +28,9 @@ def test_render_us_returns_world_trajectory(monkeypatch):
     assert np.array_equal(tr["pos"][0], np.asarray(state.pipeline_state.x.pos, np.float32))
     assert np.allclose(np.linalg.norm(tr["rot"], axis=-1), 1.0, atol=1e-5)
     assert not np.allclose(tr["pos"][5, 0], tr["pos"][0, 0])
-    # joint coordinates are consistent with the world poses: forward kinematics of (q, qd) reproduces them up to the
-    # joint separation the soft XPBD position constraints (joint_scale_pos = 0.5) leave open under load
+    # joint coordinates are consistent with the world poses: at reset forward kinematics of (q, qd) reproduces them; later
+    # the soft XPBD position constraints (joint_scale_pos = 0.5) leave a joint separation that accumulates down the chain
     from mbd_b200.model import kinematics
-    pos, rot = kinematics.forward(env.sys, tr["q"][5].astype(np.float64), tr["qd"][5].astype(np.float64))[:2]
-    assert np.allclose(pos, tr["pos"][5], atol=5e-2)
+    for t, tol in ((0, 1e-5), (5, 0.2)):
+        pos = kinematics.forward(env.sys, tr["q"][t].astype(np.float64), tr["qd"][t].astype(np.float64))[0]
+        assert np.allclose(pos, tr["pos"][t], atol=tol)
