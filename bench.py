@@ -270,6 +270,17 @@ def run_gpu(args):
             line["roofline_issue"] = {"bound": "fp32 issue slots", "achieved": wi / kern_s, "peak": peak_issue, "unit": "warp-inst/s",
                                       "frac": wi / kern_s / peak_issue, "warp_instructions_per_launch": wi,
                                       "source": "profiles/rollout_kernel_summary.json (ncu smsp__inst_executed.sum)"}
+        # fp32 roofline from the ALGORITHMIC flop count (9336 per sample and XPBD substep on humanoidrun, counted by running
+        # the physics with an operation-counting scalar type: tests/test_pk_host.py::test_algorithmic_operation_count)
+        try:
+            clk_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+            flop = float(e.n_local) * HSAMPLE * NFRAMES * 9336.0
+            peak_tf = 148 * 128 * 2 * clk_mhz * 1e6 / 1e12   # 128 fp32 lanes per SM, FMA = 2 flop
+            line["roofline_fp32"] = {"bound": "fp32 pipe", "achieved": flop / kern_s / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                                     "frac": flop / kern_s / 1e12 / peak_tf, "flop_per_sample_substep": 9336,
+                                     "note": "algorithmic flops (mul, add 1; fma 2; div, rcp, sqrt 1); the device executes ~15 % more"}
+        except Exception:  # noqa: BLE001 - never lose the bench line over an explanatory field
+            pass
         if world == 1 and not args.no_cpu_baseline:
             val, tcpu, threads = time_cpu_oracle(args.cpu_samples, 3, 1)
             line["cpu_baseline"] = {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
