@@ -28,15 +28,14 @@ def lib():
     if _LIB is not None:
         return _LIB
     path = _build.OUT
-    # Build only when the library is MISSING (a fresh clone).  A copied tree can carry arbitrary mtimes, and N ranks
-    # starting together must never race to rewrite the same .so; staleness is handled by `python -m mbd_b200.build`
-    # / __graft_entry__.build(), or by setting MBD_REBUILD=1.
-    if not os.path.exists(path) or (os.environ.get("MBD_REBUILD") == "1" and _build.is_stale()):
+    # Build when the library is missing OR was built from other sources (content hash stored beside the .so: copied
+    # trees carry arbitrary mtimes, so mtimes are not consulted).  build(force=False) re-checks inside an exclusive file
+    # lock, so of N ranks starting together exactly one compiles and the others load the finished file.
+    if _build.is_stale():
         try:
-            path = _build.build(force=True)
+            path = _build.build(force=False)
         except Exception as e:  # noqa: BLE001
-            if not os.path.exists(path):
-                raise MbdError(f"libmbd_b200.so is missing and could not be built ({e}); there is no CPU fallback") from e
+            raise MbdError(f"libmbd_b200.so is missing or stale and could not be built ({e}); there is no CPU fallback") from e
     L = ctypes.CDLL(path)
     L.mbd_last_error.restype = ctypes.c_char_p
     L.mbd_device_count.restype = ctypes.c_int

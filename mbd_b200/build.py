@@ -17,8 +17,32 @@ ROOT = os.path.dirname(PKG)
 SRC = os.path.join(PKG, "csrc", "mbd_b200.cu")
 OUT_DIR = os.path.join(PKG, "_C")
 OUT = os.path.join(OUT_DIR, "libmbd_b200.so")
-DEPS = [SRC, os.path.join(PKG, "csrc", "xpbd_device.cuh")] + [
-    os.path.join(ROOT, "include", h) for h in ("mbd_b200.h", "mbd_fp32.h", "mbd_model.h")]
+
+
+def deps():
+    """every file the library is compiled from: all of csrc/ and all of include/ (globbed, so a new header cannot be
+    forgotten — round 1 shipped a list that missed the headers holding the default kernels)"""
+    import glob
+    return sorted(glob.glob(os.path.join(PKG, "csrc", "*.cu")) + glob.glob(os.path.join(PKG, "csrc", "*.cuh"))
+                  + glob.glob(os.path.join(ROOT, "include", "*.h")) + [os.path.abspath(__file__)])
+
+
+def source_hash() -> str:
+    """sha256 over the sources and the compiler flags; stored next to the .so so that `lib()` can refuse a binary that
+    was built from other sources (copied trees carry arbitrary mtimes)."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in deps():
+        if d.endswith("build.py"):
+            continue
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS[:6]).encode())
+    return h.hexdigest()
+
+
+HASH_FILE = os.path.join(OUT_DIR, "libmbd_b200.sha256")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false", "-lineinfo",
@@ -33,11 +57,17 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def built_hash() -> str:
+    try:
+        with open(HASH_FILE) as f:
+            return f.read().strip()
+    except OSError:
+        return ""
+
+
 def is_stale() -> bool:
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    """True when the library is missing or was built from different sources (content hash, not mtimes)."""
+    return not os.path.exists(OUT) or built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -55,6 +85,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
         os.replace(tmp, OUT)                       # atomic: a concurrent reader never sees a half-written library
+        with open(HASH_FILE + f".tmp{os.getpid()}", "w") as f:
+            f.write(source_hash() + "\n")
+        os.replace(HASH_FILE + f".tmp{os.getpid()}", HASH_FILE)
         if verbose:
             print(res.stderr)
     return OUT
