@@ -101,6 +101,7 @@ struct RolloutArgs {
   // multi-group CTAs: warp -> (group << 4) | link slot
   signed char gw[32];
   int count_x;             // group barriers: 32 * (links that are not leaves with contacts), see SyncGroup
+  int stagger;             // two-group CTA: cycles group 1 waits before its first step (experiment: de-phase the groups)
 };
 
 template <bool FUSED, int CMAX>
@@ -239,7 +240,7 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
 
   static_assert(SPLIT == 1 || SPLIT == 2, "links per warp");
   static_assert(SPLIT == 1 || SYNC == 0, "edge barriers assume one link per warp");
-  static_assert(GROUPS == 1 || (SPLIT == 1 && SYNC == 0), "sample groups: one link per warp, group barriers");
+  static_assert(GROUPS == 1 || (SPLIT == 1 && (SYNC == 0 || SYNC == 3)), "sample groups: one link per warp, group or neighbourhood barriers");
   constexpr int kLpl = kWplLanes / SPLIT;                      // lanes (= samples) per link
   const int tid = threadIdx.x, lane = tid & 31;
   // GROUPS independent 32-sample groups share the CTA with their warps INTERLEAVED (warp w -> group w % GROUPS,
@@ -293,9 +294,10 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
     s.v = V3(st[10], st[11], st[12]);
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
-  typename std::conditional<GROUPS != 1, SyncGroup<kGroupLinks>,
+  typename std::conditional<GROUPS != 1, typename std::conditional<SYNC == 3, SyncHood, SyncGroup<kGroupLinks>>::type,
       typename std::conditional<SYNC == 1, SyncP2P, typename std::conditional<SYNC == 2, SyncNamed, SyncCta>::type>::type>::type Y;
-  if constexpr (GROUPS != 1) { Y.base = 1 + 4 * grp; Y.count_x = a.count_x; }
+  if constexpr (GROUPS != 1 && SYNC == 3) Y.setup(M, l, L, 1 + 7 * grp, 7);
+  if constexpr (GROUPS != 1 && SYNC != 3) { Y.base = 1 + 4 * grp; Y.count_x = a.count_x; }
   if constexpr (SYNC == 2) Y.setup(M, l, L);
   if constexpr (SYNC == 1) {
     Y.pose = edge_bars; Y.terms = edge_bars + MBD_MAXL; Y.ph_pose = 0u; Y.ph_terms = 0u;
@@ -310,6 +312,12 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
     if (M.hi(MBD_H_TRACK0 + k) == l) my_track = k;
   __syncthreads();
   if constexpr (SYNC != 0) Y.arrive_pose(l);  // the initial pose is published
+  if constexpr (GROUPS != 1) {
+    if (grp == 1 && a.stagger > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)a.stagger) {}
+    }
+  }
   float rsum = 0.0f, tacc = 0.0f;
   const float* urow = a.Y0s + (size_t)n_rd * HNu;
   for (int t = 0; t < a.H; ++t) {
@@ -1040,6 +1048,7 @@ static void build_pairing(mbd_model* m, const uint32_t* blob) {
     if (!used[a]) add_pair(a, -1);
 }
 
+static int g_group_stagger = 0;   // cycles, see RolloutArgs::stagger
 static int g_kernel_variant = 0;  // 0 = auto, 1 = v1 (lane per link), 2..4 = v2 (warp per link; CTA / named / mbarrier sync)
 static thread_local char g_err[256] = "";
 static int set_err(const char* where, cudaError_t e) {
@@ -1063,7 +1072,7 @@ int mbd_device_count(void) {
 }
 
 int mbd_set_kernel_variant(int v) {
-  if (v < 0 || v > 9 || v == 7) return MBD_EINVAL;
+  if (v < 0 || v > 10 || v == 7) return MBD_EINVAL;
   g_kernel_variant = v;
   return MBD_OK;
 }
@@ -1085,6 +1094,12 @@ int mbd_model_set_group_map(mbd_model* m, const int* map, int n) {
     seen[g][sl] = 1;
   }
   for (int w = 0; w < n; ++w) m->gw2[w] = (signed char)map[w];
+  return MBD_OK;
+}
+
+int mbd_set_group_stagger(int cycles) {
+  if (cycles < 0) return MBD_EINVAL;
+  g_group_stagger = cycles;
   return MBD_OK;
 }
 
@@ -1198,18 +1213,26 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
       else MBD_LAUNCH_WPL(MBD_MAXL, 1, 0, 2, grid, 32 * nw);
     } else {
       int grid = (a.n + mbd::kWplLanes - 1) / mbd::kWplLanes;
-      if (L == 11 && variant == 6 && m->max_ncon <= 2) {  // two interleaved 32-sample groups per 704-thread CTA
+      if (L == 11 && (variant == 6 || variant == 10) && m->max_ncon <= 2) {  // two interleaved 32-sample groups per 704-thread CTA
         int grid2 = (a.n + 63) / 64;
         size_t dyn2 = 2 * dyn;
         memcpy(a.wl, m->wl6, sizeof(a.wl));
+        a.stagger = g_group_stagger;
         static bool attr_set = false;
         if (!attr_set) {
           CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
           CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+          CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<true, 22, 1, 3, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+          CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<false, 22, 1, 3, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
           attr_set = true;
         }
-        if (fused) mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
-        else mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+        if (variant == 10) {   // neighbourhood barriers (SyncHood)
+          if (fused) mbd::k_rollout_wpl<true, 22, 1, 3, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+          else mbd::k_rollout_wpl<false, 22, 1, 3, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+        } else {
+          if (fused) mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+          else mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+        }
       } else if (L == 11 && variant == 2) MBD_LAUNCH_WPL(11, 2, 0, 1, grid, 32 * L);       // CTA-wide barriers
       else if (L == 11 && variant == 3 && grid <= 148) MBD_LAUNCH_WPL(11, 1, 2, 1, grid, 32 * L);  // one CTA per SM: no register cap
       else if (L == 11 && variant == 3) MBD_LAUNCH_WPL(11, 2, 2, 1, grid, 32 * L);  // named edge barriers
