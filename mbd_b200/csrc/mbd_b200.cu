@@ -490,8 +490,9 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
     s.v = pk::mkV(b(10), b(11), b(12));
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
-  typename std::conditional<SYNC == 2, SyncNamed, SyncGroup<kPkLinks>>::type Y;
+  typename std::conditional<SYNC == 2, SyncNamed, typename std::conditional<SYNC == 3, SyncHood, SyncGroup<kPkLinks>>::type>::type Y;
   if constexpr (SYNC == 2) Y.setup(Ms, l, L);
+  else if constexpr (SYNC == 3) Y.setup(Ms, l, L, 1, 15);
   else { Y.base = 1; Y.count_x = a.count_x; }
   int my_track = -1;
   for (int k = 0; k < ntrack; ++k)
@@ -1072,7 +1073,7 @@ int mbd_device_count(void) {
 }
 
 int mbd_set_kernel_variant(int v) {
-  if (v < 0 || v > 10 || v == 7) return MBD_EINVAL;
+  if (v < 0 || v > 11 || v == 7) return MBD_EINVAL;
   g_kernel_variant = v;
   return MBD_OK;
 }
@@ -1177,9 +1178,9 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   // named edge barriers; two CTAs per SM (> 148 CTAs) favour plain CTA barriers (better I-cache locality)
   // beyond one 32-sample CTA per SM: two interleaved groups per 704-thread CTA (critical links get the highest warp ids)
   if (variant == 0) variant = (L == 11) ? (a.n < 2048 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 6 : 2))) : 2;
-  if ((variant == 8 || variant == 9) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
-  if (variant == 8 || variant == 9) {
-    // packed kernel: 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
+  if ((variant == 8 || variant == 9 || variant == 11) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
+  if (variant == 8 || variant == 9 || variant == 11) {
+    // packed kernel (11: neighbourhood barriers): 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
     memcpy(a.wl, m->wl1, sizeof(a.wl));
     a.count_x = 32 * (L - m->nlate);
     const int grid = (a.n + mbd::kPkSamples - 1) / mbd::kPkSamples;
@@ -1194,10 +1195,11 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
     if (!pk_attr_set) {
       MBD_PK_ATTR(true, 2, 0); MBD_PK_ATTR(false, 2, 0); MBD_PK_ATTR(true, 2, 2); MBD_PK_ATTR(false, 2, 2);
       MBD_PK_ATTR(true, MBD_MAXCON, 0); MBD_PK_ATTR(false, MBD_MAXCON, 0); MBD_PK_ATTR(true, MBD_MAXCON, 2); MBD_PK_ATTR(false, MBD_MAXCON, 2);
+      MBD_PK_ATTR(true, 2, 3); MBD_PK_ATTR(false, 2, 3); MBD_PK_ATTR(true, MBD_MAXCON, 3); MBD_PK_ATTR(false, MBD_MAXCON, 3);
       pk_attr_set = true;
     }
-    if (m->max_ncon <= 2) { if (variant == 8) MBD_PK_LAUNCH(2, 0); else MBD_PK_LAUNCH(2, 2); }
-    else { if (variant == 8) MBD_PK_LAUNCH(MBD_MAXCON, 0); else MBD_PK_LAUNCH(MBD_MAXCON, 2); }
+    if (m->max_ncon <= 2) { if (variant == 8) MBD_PK_LAUNCH(2, 0); else if (variant == 9) MBD_PK_LAUNCH(2, 2); else MBD_PK_LAUNCH(2, 3); }
+    else { if (variant == 8) MBD_PK_LAUNCH(MBD_MAXCON, 0); else if (variant == 9) MBD_PK_LAUNCH(MBD_MAXCON, 2); else MBD_PK_LAUNCH(MBD_MAXCON, 3); }
 #undef MBD_PK_ATTR
 #undef MBD_PK_LAUNCH
   } else if (variant >= 2) {

@@ -37,9 +37,10 @@ if __name__ == "__main__":
     if len(sys.argv) == 4:
         child(int(sys.argv[1]), sys.argv[2], int(sys.argv[3]))
     else:
-        for variant in (6, 10):
-            for mp in ("A", "B"):
-                for stagger in (0, 1500, 3000, 4500):
+        cases = [(v, mp, st) for v in (6, 10) for mp in ("A", "B") for st in (0, 1500, 3000, 4500)] + [(v, "A", 0) for v in (8, 9, 11)]
+        for variant, mp, stagger in cases:
+            if True:
+                if True:
                     try:
                         subprocess.run([sys.executable, os.path.abspath(__file__), str(variant), mp, str(stagger)], timeout=40, check=False)
                     except subprocess.TimeoutExpired:
