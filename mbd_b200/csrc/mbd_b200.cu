@@ -183,11 +183,14 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
       v3 v0 = link_origin_vel(M, c, s);
       r_pre = 1.0f + ((-fabsf(v0.x - 1.6f) - fabsf(x0.z - 1.3f)) - fabsf(x0.y) * 0.1f);
     }
+    if (reward_kind == MBD_REWARD_ANT && c.l == 0) r_pre = link_origin(M, c, s).x;   // root x before the step
     for (int f = 0; f < nsub; ++f) positional_step<CMAX>(M, c, K, s, tau);
     if (c.l == 0) {
       float r;
       if (reward_kind == MBD_REWARD_HUMANOIDTRACK) {
         r = r_pre;
+      } else if (reward_kind == MBD_REWARD_ANT) {
+        r = reward_ant(M, r_pre, link_origin(M, c, s).x, urow + t * nu, nu);
       } else {
         r = reward_post(reward_kind, link_origin(M, c, s));
       }
@@ -334,11 +337,14 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
       v3 v0 = link_origin_vel_w(M, 0, s);
       r_pre = 1.0f + ((-fabsf(v0.x - 1.6f) - fabsf(x0.z - 1.3f)) - fabsf(x0.y) * 0.1f);
     }
+    if (reward_kind == MBD_REWARD_ANT && l == 0) r_pre = link_origin_w(M, 0, s).x;   // root x before the step
     for (int f = 0; f < nsub; ++f) positional_step_wpl<CMAX>(M, c, S, Y, s, tau);
     if (l == 0) {
       float r;
       if (reward_kind == MBD_REWARD_HUMANOIDTRACK) {
         r = r_pre;
+      } else if (reward_kind == MBD_REWARD_ANT) {
+        r = reward_ant(M, r_pre, link_origin_w(M, 0, s).x, urow + t * nu, nu);
       } else {
         r = reward_post(reward_kind, link_origin_w(M, 0, s));
       }
@@ -521,10 +527,18 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
       rp0 = 1.0f + ((-fabsf(va.x - 1.6f) - fabsf(xa.z - 1.3f)) - fabsf(xa.y) * 0.1f);
       rp1 = 1.0f + ((-fabsf(vb.x - 1.6f) - fabsf(xb.z - 1.3f)) - fabsf(xb.y) * 0.1f);
     }
+    if (reward_kind == MBD_REWARD_ANT && l == 0) {   // root x before the step
+      pk::V<pk::f2> x0 = pk::link_origin_w(M, 0, s);
+      rp0 = pk::lo(x0.x); rp1 = pk::hi(x0.x);
+    }
     for (int f = 0; f < nsub; ++f) positional_step_pk<CMAX>(M, c, S, Y, s, tau);
     if (l == 0) {
       float ra = rp0, rb = rp1;
-      if (reward_kind != MBD_REWARD_HUMANOIDTRACK) {
+      if (reward_kind == MBD_REWARD_ANT) {
+        pk::V<pk::f2> x0 = pk::link_origin_w(M, 0, s);
+        ra = reward_ant(Ms, rp0, pk::lo(x0.x), urow0 + t * nu, nu);
+        rb = reward_ant(Ms, rp1, pk::hi(x0.x), urow1 + t * nu, nu);
+      } else if (reward_kind != MBD_REWARD_HUMANOIDTRACK) {
         pk::V<pk::f2> x0 = pk::link_origin_w(M, 0, s);
         ra = reward_post(reward_kind, pk_lo(x0));
         rb = reward_post(reward_kind, pk_hi(x0));
