@@ -34,11 +34,14 @@ int mbd_device_count(void);
  * warp, lane = sample) with CTA-wide / named-barrier / mbarrier phase synchronisation, 5 = v2 with two
  * same-type links per warp (16 samples per CTA), 6 = v2 with two interleaved 32-sample groups per 704-thread CTA
  * (leaf links decoupled from the group barriers), 8/9 = packed kernel: two samples per lane on FFMA2/FMUL2/FADD2,
- * 64 samples per CTA, group barriers / named edge barriers (11-link models; others fall back to 2).  7 is unused.
+ * 64 samples per CTA, group barriers / named edge barriers (11-link models; others fall back to 2), 10 = 6 with
+ * neighbourhood barriers (one rendezvous id per parent node).  7 is unused.
  * All variants produce bit-identical results; the switch exists for tests and profiling. */
 int mbd_set_kernel_variant(int v);
 /* tuning hook: slot -> link order of the one-link-per-warp mapping (slot L-1 gets the highest warp id) */
 int mbd_model_set_warp_order(mbd_model* m, const int* order, int n);
+/* tuning hook: cycles the second sample group of a two-group CTA waits before its first step (de-phases the groups) */
+int mbd_set_group_stagger(int cycles);
 /* tuning hook: two-group CTA warp table, map[w] = (group << 4) | slot for the 2*L warps */
 int mbd_model_set_group_map(mbd_model* m, const int* map, int n);
 

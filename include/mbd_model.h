@@ -50,7 +50,8 @@ enum {
   MBD_HDR_WORDS = 64
 };
 
-enum { MBD_REWARD_HUMANOIDRUN = 0, MBD_REWARD_HUMANOIDTRACK = 1, MBD_REWARD_HOPPER = 2, MBD_REWARD_HUMANOIDSTANDUP = 3 };
+enum { MBD_REWARD_HUMANOIDRUN = 0, MBD_REWARD_HUMANOIDTRACK = 1, MBD_REWARD_HOPPER = 2, MBD_REWARD_HUMANOIDSTANDUP = 3,
+       MBD_REWARD_ANT = 4 /* RW0 = env dt (sys.dt * n_frames), RW0+1 = healthy reward, RW0+2 = control cost weight */ };
 
 /* ---- per-link fields ------------------------------------------------------------- */
 enum {

@@ -101,6 +101,7 @@ struct RolloutArgs {
   // multi-group CTAs: warp -> (group << 4) | link slot
   signed char gw[32];
   int count_x;             // group barriers: 32 * (links that are not leaves with contacts), see SyncGroup
+  int stagger;             // two-group CTA: cycles group 1 waits before its first step (experiment: de-phase the groups)
 };
 
 template <bool FUSED, int CMAX>
@@ -182,11 +183,14 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
       v3 v0 = link_origin_vel(M, c, s);
       r_pre = 1.0f + ((-fabsf(v0.x - 1.6f) - fabsf(x0.z - 1.3f)) - fabsf(x0.y) * 0.1f);
     }
+    if (reward_kind == MBD_REWARD_ANT && c.l == 0) r_pre = link_origin(M, c, s).x;   // root x before the step
     for (int f = 0; f < nsub; ++f) positional_step<CMAX>(M, c, K, s, tau);
     if (c.l == 0) {
       float r;
       if (reward_kind == MBD_REWARD_HUMANOIDTRACK) {
         r = r_pre;
+      } else if (reward_kind == MBD_REWARD_ANT) {
+        r = reward_ant(M, r_pre, link_origin(M, c, s).x, urow + t * nu, nu);
       } else {
         r = reward_post(reward_kind, link_origin(M, c, s));
       }
@@ -239,7 +243,7 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
 
   static_assert(SPLIT == 1 || SPLIT == 2, "links per warp");
   static_assert(SPLIT == 1 || SYNC == 0, "edge barriers assume one link per warp");
-  static_assert(GROUPS == 1 || (SPLIT == 1 && SYNC == 0), "sample groups: one link per warp, group barriers");
+  static_assert(GROUPS == 1 || (SPLIT == 1 && (SYNC == 0 || SYNC == 3)), "sample groups: one link per warp, group or neighbourhood barriers");
   constexpr int kLpl = kWplLanes / SPLIT;                      // lanes (= samples) per link
   const int tid = threadIdx.x, lane = tid & 31;
   // GROUPS independent 32-sample groups share the CTA with their warps INTERLEAVED (warp w -> group w % GROUPS,
@@ -293,9 +297,10 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
     s.v = V3(st[10], st[11], st[12]);
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
-  typename std::conditional<GROUPS != 1, SyncGroup<kGroupLinks>,
+  typename std::conditional<GROUPS != 1, typename std::conditional<SYNC == 3, SyncHood, SyncGroup<kGroupLinks>>::type,
       typename std::conditional<SYNC == 1, SyncP2P, typename std::conditional<SYNC == 2, SyncNamed, SyncCta>::type>::type>::type Y;
-  if constexpr (GROUPS != 1) { Y.base = 1 + 4 * grp; Y.count_x = a.count_x; }
+  if constexpr (GROUPS != 1 && SYNC == 3) Y.setup(M, l, L, 1 + 7 * grp, 7);
+  if constexpr (GROUPS != 1 && SYNC != 3) { Y.base = 1 + 4 * grp; Y.count_x = a.count_x; }
   if constexpr (SYNC == 2) Y.setup(M, l, L);
   if constexpr (SYNC == 1) {
     Y.pose = edge_bars; Y.terms = edge_bars + MBD_MAXL; Y.ph_pose = 0u; Y.ph_terms = 0u;
@@ -310,6 +315,12 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
     if (M.hi(MBD_H_TRACK0 + k) == l) my_track = k;
   __syncthreads();
   if constexpr (SYNC != 0) Y.arrive_pose(l);  // the initial pose is published
+  if constexpr (GROUPS != 1) {
+    if (grp == 1 && a.stagger > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)a.stagger) {}
+    }
+  }
   float rsum = 0.0f, tacc = 0.0f;
   const float* urow = a.Y0s + (size_t)n_rd * HNu;
   for (int t = 0; t < a.H; ++t) {
@@ -326,11 +337,14 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
       v3 v0 = link_origin_vel_w(M, 0, s);
       r_pre = 1.0f + ((-fabsf(v0.x - 1.6f) - fabsf(x0.z - 1.3f)) - fabsf(x0.y) * 0.1f);
     }
+    if (reward_kind == MBD_REWARD_ANT && l == 0) r_pre = link_origin_w(M, 0, s).x;   // root x before the step
     for (int f = 0; f < nsub; ++f) positional_step_wpl<CMAX>(M, c, S, Y, s, tau);
     if (l == 0) {
       float r;
       if (reward_kind == MBD_REWARD_HUMANOIDTRACK) {
         r = r_pre;
+      } else if (reward_kind == MBD_REWARD_ANT) {
+        r = reward_ant(M, r_pre, link_origin_w(M, 0, s).x, urow + t * nu, nu);
       } else {
         r = reward_post(reward_kind, link_origin_w(M, 0, s));
       }
@@ -482,8 +496,9 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
     s.v = pk::mkV(b(10), b(11), b(12));
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
-  typename std::conditional<SYNC == 2, SyncNamed, SyncGroup<kPkLinks>>::type Y;
+  typename std::conditional<SYNC == 2, SyncNamed, typename std::conditional<SYNC == 3, SyncHood, SyncGroup<kPkLinks>>::type>::type Y;
   if constexpr (SYNC == 2) Y.setup(Ms, l, L);
+  else if constexpr (SYNC == 3) Y.setup(Ms, l, L, 1, 15);
   else { Y.base = 1; Y.count_x = a.count_x; }
   int my_track = -1;
   for (int k = 0; k < ntrack; ++k)
@@ -512,10 +527,18 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
       rp0 = 1.0f + ((-fabsf(va.x - 1.6f) - fabsf(xa.z - 1.3f)) - fabsf(xa.y) * 0.1f);
       rp1 = 1.0f + ((-fabsf(vb.x - 1.6f) - fabsf(xb.z - 1.3f)) - fabsf(xb.y) * 0.1f);
     }
+    if (reward_kind == MBD_REWARD_ANT && l == 0) {   // root x before the step
+      pk::V<pk::f2> x0 = pk::link_origin_w(M, 0, s);
+      rp0 = pk::lo(x0.x); rp1 = pk::hi(x0.x);
+    }
     for (int f = 0; f < nsub; ++f) positional_step_pk<CMAX>(M, c, S, Y, s, tau);
     if (l == 0) {
       float ra = rp0, rb = rp1;
-      if (reward_kind != MBD_REWARD_HUMANOIDTRACK) {
+      if (reward_kind == MBD_REWARD_ANT) {
+        pk::V<pk::f2> x0 = pk::link_origin_w(M, 0, s);
+        ra = reward_ant(Ms, rp0, pk::lo(x0.x), urow0 + t * nu, nu);
+        rb = reward_ant(Ms, rp1, pk::hi(x0.x), urow1 + t * nu, nu);
+      } else if (reward_kind != MBD_REWARD_HUMANOIDTRACK) {
         pk::V<pk::f2> x0 = pk::link_origin_w(M, 0, s);
         ra = reward_post(reward_kind, pk_lo(x0));
         rb = reward_post(reward_kind, pk_hi(x0));
@@ -1040,6 +1063,7 @@ static void build_pairing(mbd_model* m, const uint32_t* blob) {
     if (!used[a]) add_pair(a, -1);
 }
 
+static int g_group_stagger = 0;   // cycles, see RolloutArgs::stagger
 static int g_kernel_variant = 0;  // 0 = auto, 1 = v1 (lane per link), 2..4 = v2 (warp per link; CTA / named / mbarrier sync)
 static thread_local char g_err[256] = "";
 static int set_err(const char* where, cudaError_t e) {
@@ -1063,7 +1087,7 @@ int mbd_device_count(void) {
 }
 
 int mbd_set_kernel_variant(int v) {
-  if (v < 0 || v > 9 || v == 7) return MBD_EINVAL;
+  if (v < 0 || v > 11 || v == 7) return MBD_EINVAL;
   g_kernel_variant = v;
   return MBD_OK;
 }
@@ -1085,6 +1109,12 @@ int mbd_model_set_group_map(mbd_model* m, const int* map, int n) {
     seen[g][sl] = 1;
   }
   for (int w = 0; w < n; ++w) m->gw2[w] = (signed char)map[w];
+  return MBD_OK;
+}
+
+int mbd_set_group_stagger(int cycles) {
+  if (cycles < 0) return MBD_EINVAL;
+  g_group_stagger = cycles;
   return MBD_OK;
 }
 
@@ -1162,9 +1192,9 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   // named edge barriers; two CTAs per SM (> 148 CTAs) favour plain CTA barriers (better I-cache locality)
   // beyond one 32-sample CTA per SM: two interleaved groups per 704-thread CTA (critical links get the highest warp ids)
   if (variant == 0) variant = (L == 11) ? (a.n < 2048 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 6 : 2))) : 2;
-  if ((variant == 8 || variant == 9) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
-  if (variant == 8 || variant == 9) {
-    // packed kernel: 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
+  if ((variant == 8 || variant == 9 || variant == 11) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
+  if (variant == 8 || variant == 9 || variant == 11) {
+    // packed kernel (11: neighbourhood barriers): 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
     memcpy(a.wl, m->wl1, sizeof(a.wl));
     a.count_x = 32 * (L - m->nlate);
     const int grid = (a.n + mbd::kPkSamples - 1) / mbd::kPkSamples;
@@ -1179,10 +1209,11 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
     if (!pk_attr_set) {
       MBD_PK_ATTR(true, 2, 0); MBD_PK_ATTR(false, 2, 0); MBD_PK_ATTR(true, 2, 2); MBD_PK_ATTR(false, 2, 2);
       MBD_PK_ATTR(true, MBD_MAXCON, 0); MBD_PK_ATTR(false, MBD_MAXCON, 0); MBD_PK_ATTR(true, MBD_MAXCON, 2); MBD_PK_ATTR(false, MBD_MAXCON, 2);
+      MBD_PK_ATTR(true, 2, 3); MBD_PK_ATTR(false, 2, 3); MBD_PK_ATTR(true, MBD_MAXCON, 3); MBD_PK_ATTR(false, MBD_MAXCON, 3);
       pk_attr_set = true;
     }
-    if (m->max_ncon <= 2) { if (variant == 8) MBD_PK_LAUNCH(2, 0); else MBD_PK_LAUNCH(2, 2); }
-    else { if (variant == 8) MBD_PK_LAUNCH(MBD_MAXCON, 0); else MBD_PK_LAUNCH(MBD_MAXCON, 2); }
+    if (m->max_ncon <= 2) { if (variant == 8) MBD_PK_LAUNCH(2, 0); else if (variant == 9) MBD_PK_LAUNCH(2, 2); else MBD_PK_LAUNCH(2, 3); }
+    else { if (variant == 8) MBD_PK_LAUNCH(MBD_MAXCON, 0); else if (variant == 9) MBD_PK_LAUNCH(MBD_MAXCON, 2); else MBD_PK_LAUNCH(MBD_MAXCON, 3); }
 #undef MBD_PK_ATTR
 #undef MBD_PK_LAUNCH
   } else if (variant >= 2) {
@@ -1198,18 +1229,26 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
       else MBD_LAUNCH_WPL(MBD_MAXL, 1, 0, 2, grid, 32 * nw);
     } else {
       int grid = (a.n + mbd::kWplLanes - 1) / mbd::kWplLanes;
-      if (L == 11 && variant == 6 && m->max_ncon <= 2) {  // two interleaved 32-sample groups per 704-thread CTA
+      if (L == 11 && (variant == 6 || variant == 10) && m->max_ncon <= 2) {  // two interleaved 32-sample groups per 704-thread CTA
         int grid2 = (a.n + 63) / 64;
         size_t dyn2 = 2 * dyn;
         memcpy(a.wl, m->wl6, sizeof(a.wl));
+        a.stagger = g_group_stagger;
         static bool attr_set = false;
         if (!attr_set) {
           CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
           CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+          CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<true, 22, 1, 3, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+          CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<false, 22, 1, 3, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
           attr_set = true;
         }
-        if (fused) mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
-        else mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+        if (variant == 10) {   // neighbourhood barriers (SyncHood)
+          if (fused) mbd::k_rollout_wpl<true, 22, 1, 3, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+          else mbd::k_rollout_wpl<false, 22, 1, 3, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+        } else {
+          if (fused) mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+          else mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+        }
       } else if (L == 11 && variant == 2) MBD_LAUNCH_WPL(11, 2, 0, 1, grid, 32 * L);       // CTA-wide barriers
       else if (L == 11 && variant == 3 && grid <= 148) MBD_LAUNCH_WPL(11, 1, 2, 1, grid, 32 * L);  // one CTA per SM: no register cap
       else if (L == 11 && variant == 3) MBD_LAUNCH_WPL(11, 2, 2, 1, grid, 32 * L);  // named edge barriers

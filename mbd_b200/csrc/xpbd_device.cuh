@@ -406,6 +406,16 @@ __device__ __forceinline__ float reward_post(int kind, v3 x0) {
   return x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;  // hopper.py:57-65
 }
 
+// brax/envs/ant.py reward (oracle/mbd_oracle.c::reward_ant): forward velocity of the root + healthy reward - control cost;
+// u = this sample's action row of the env step
+__device__ __forceinline__ float reward_ant(const ModelSmem& M, float x_before, float x_after, const float* u, int nu) {
+  const float env_dt = M.hf(MBD_H_RW0), healthy = M.hf(MBD_H_RW0 + 1), wc = M.hf(MBD_H_RW0 + 2);
+  float fwd = (x_after - x_before) / env_dt;
+  float ss = 0.0f;
+  for (int k = 0; k < nu; ++k) ss = ss + u[k] * u[k];
+  return (fwd + healthy) - wc * ss;
+}
+
 // com.to_world pieces
 __device__ __forceinline__ v3 link_origin(const ModelSmem& M, const LaneCfg& c, const LinkState& s) {
   return vsub(s.p, vrotate(M.l3(MBD_F_COM, c.l < MBD_MAXL ? c.l : 0), s.q));

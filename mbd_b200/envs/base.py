@@ -86,10 +86,15 @@ class PipelineEnv:
         self.backend = backend
         self._n_frames = n_frames
         self._links = list(range(sys.num_links())) if self.sim_links is None else list(self.sim_links)
-        self.blob = blob_mod.pack(sys, n_frames, self.reward_kind, links=self._links, track_links=tuple(self.track_links))
+        self.blob = blob_mod.pack(sys, n_frames, self.reward_kind, links=self._links, track_links=tuple(self.track_links),
+                                  **self._pack_kwargs())
         self._models: Dict[int, ops.Model] = {}
         # world poses of links that are NOT simulated (cosmetic bodies) stay at their init_q pose
         self._static_x = kinematics.forward(sys, sys.init_q, np.zeros(sys.qd_size()))
+
+    def _pack_kwargs(self):
+        """extra keyword arguments for blob.pack (reward parameters)"""
+        return {}
 
     # ---- brax PipelineEnv API ---------------------------------------------------------------
     @property

@@ -37,7 +37,7 @@ D_STIFF, D_DAMP, D_LO, D_HI, D_ACT, D_GEAR, D_CLO, D_CHI = range(8)
 BLOB_WORDS = HDR_WORDS + NFIELDS * MAXL
 STATE_STRIDE = 13
 
-REWARD_HUMANOIDRUN, REWARD_HUMANOIDTRACK, REWARD_HOPPER, REWARD_HUMANOIDSTANDUP = 0, 1, 2, 3
+REWARD_HUMANOIDRUN, REWARD_HUMANOIDTRACK, REWARD_HOPPER, REWARD_HUMANOIDSTANDUP, REWARD_ANT = 0, 1, 2, 3, 4
 
 _BIG = 3.0e38  # stands in for +-inf limits (keeps the arithmetic NaN-free)
 

@@ -430,6 +430,17 @@ static float reward_post(const Model* m, const Link* s) {
   }
   return 0.0f;
 }
+/* brax/envs/ant.py [brax-recalled; the env is Brax's stock one, /root/reference/mbd/envs/__init__.py:30-31]:
+ *   velocity = (x.pos[0] - x0.pos[0]) / dt;  reward = forward_reward + healthy_reward - ctrl_cost - contact_cost
+ * with healthy_reward paid unconditionally (terminate_when_unhealthy=True), contact cost off, ctrl_cost =
+ * weight * sum(action^2) on the action handed to env.step.  Sum of squares taken in action order. */
+static float reward_ant(const Model* m, float x_before, float x_after, const float* u) {
+  const float env_dt = m->f[MBD_H_RW0], healthy = m->f[MBD_H_RW0 + 1], wc = m->f[MBD_H_RW0 + 2];
+  float fwd = (x_after - x_before) / env_dt;
+  float ss = 0.0f;
+  for (int k = 0; k < m->nu; ++k) ss = ss + u[k] * u[k];
+  return (fwd + healthy) - wc * ss;
+}
 static float reward_pre(const Model* m, const Link* s) {
   /* humanoidtrack.py:87-96 — evaluated on the state BEFORE the step */
   v3 x0 = link_origin(m, s, 0);
@@ -479,8 +490,10 @@ ORC_API int orc_xpbd_rollout(const uint32_t* blob, const float* state_init, cons
     for (int t = 0; t < H; ++t) {
       const float* u = Y0s + ((size_t)i * H + t) * nu;
       float r_pre = (m.reward == MBD_REWARD_HUMANOIDTRACK) ? reward_pre(&m, s) : 0.0f;
+      const float x_before = (m.reward == MBD_REWARD_ANT) ? link_origin(&m, s, 0).x : 0.0f;
       for (int f = 0; f < nsub; ++f) positional_step(&m, s, u); /* PipelineEnv.pipeline_step */
-      float r = (m.reward == MBD_REWARD_HUMANOIDTRACK) ? r_pre : reward_post(&m, s);
+      float r = (m.reward == MBD_REWARD_HUMANOIDTRACK) ? r_pre
+                : (m.reward == MBD_REWARD_ANT) ? reward_ant(&m, x_before, link_origin(&m, s, 0).x, u) : reward_post(&m, s);
       if (rewss) rewss[(size_t)i * H + t] = r;
       sum += r;
       for (int k = 0; k < m.ntrack; ++k) {
