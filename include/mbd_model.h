@@ -50,13 +50,16 @@ enum {
   MBD_HDR_WORDS = 64
 };
 
-enum { MBD_REWARD_HUMANOIDRUN = 0, MBD_REWARD_HUMANOIDTRACK = 1, MBD_REWARD_HOPPER = 2, MBD_REWARD_HUMANOIDSTANDUP = 3,
-       MBD_REWARD_ANT = 4 /* RW0 = env dt (sys.dt * n_frames), RW0+1 = healthy reward, RW0+2 = control cost weight */ };
+enum { MBD_REWARD_HUMANOIDRUN = 0, MBD_REWARD_HUMANOIDTRACK = 1,
+       MBD_REWARD_HOPPER = 2,  /* x - 0.5 clip(|z - RW0|, -1, 1): hopper (RW0 = 1.0) and walker2d (RW0 = 1.1) */
+       MBD_REWARD_HUMANOIDSTANDUP = 3,
+       MBD_REWARD_ANT = 4,     /* (x' - x)/RW0 + RW1 - RW2 |a|^2: ant (RW1 healthy 1, RW2 0.5) and halfcheetah (RW1 0, RW2 0.1); RW0 = env dt */
+       MBD_REWARD_CARTPOLE = 5 /* cos(q[1]) - |qd[0]|: pole angle about its hinge axis, cart slide velocity (cartpole.py:44) */ };
 
 /* ---- per-link fields ------------------------------------------------------------- */
 enum {
   MBD_F_PARENT = 0,    /* int  (-1 = world) */
-  MBD_F_NDOF,          /* int  0 = free root, 1..3 stacked hinges */
+  MBD_F_NDOF,          /* int  0 = free root, 1..3 stacked 1-dof joints (hinges; slides only on world-parented links) */
   MBD_F_CHILD0,        /* int[MBD_MAXCHILD] ascending link ids, -1 = none */
   MBD_F_MASS = MBD_F_CHILD0 + MBD_MAXCHILD,
   MBD_F_INV_MASS,
@@ -69,7 +72,8 @@ enum {
   MBD_F_PQ = MBD_F_RP + 3,    /* float[4] joint frame rotation in the parent link frame */
   MBD_F_PARITY = MBD_F_PQ + 4,
   MBD_F_ANG_DAMP,      /* constraint_ang_damping */
-  MBD_F_DOF0,          /* 3 x {stiffness, damping, lo, hi, act_id(int), gear, ctrl_lo, ctrl_hi} */
+  MBD_F_SLIDE,         /* int  bit k set: dof k of the link is a slide (prismatic) dof; only on links whose parent is the world */
+  MBD_F_DOF0,          /* 3 x {stiffness, damping, lo, hi, act_id(int), gear, ctrl_lo, ctrl_hi} (lo/hi: radians, or metres for a slide) */
   MBD_F_NCON = MBD_F_DOF0 + MBD_MAXDOF * MBD_DOF_STRIDE, /* int */
   MBD_F_CON0,          /* MBD_MAXCON x {sx, sy, sz (sphere centre - com, link frame), radius, friction} */
   MBD_NFIELDS = MBD_F_CON0 + MBD_MAXCON * MBD_CON_STRIDE

@@ -185,12 +185,17 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
     }
     if (reward_kind == MBD_REWARD_ANT && c.l == 0) r_pre = link_origin(M, c, s).x;   // root x before the step
     for (int f = 0; f < nsub; ++f) positional_step<CMAX>(M, c, K, s, tau);
+    const q4 q_link1 = shfl4(s.q, c.gbase + 1);   // cartpole reward: the pole's rotation (all lanes shuffle)
     if (c.l == 0) {
       float r;
       if (reward_kind == MBD_REWARD_HUMANOIDTRACK) {
         r = r_pre;
       } else if (reward_kind == MBD_REWARD_ANT) {
         r = reward_ant(M, r_pre, link_origin(M, c, s).x, urow + t * nu, nu);
+      } else if (reward_kind == MBD_REWARD_HOPPER) {
+        r = reward_hopper(M, link_origin(M, c, s));
+      } else if (reward_kind == MBD_REWARD_CARTPOLE) {
+        r = reward_cartpole(M, s, q_link1);
       } else {
         r = reward_post(reward_kind, link_origin(M, c, s));
       }
@@ -345,6 +350,10 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
         r = r_pre;
       } else if (reward_kind == MBD_REWARD_ANT) {
         r = reward_ant(M, r_pre, link_origin_w(M, 0, s).x, urow + t * nu, nu);
+      } else if (reward_kind == MBD_REWARD_HOPPER) {
+        r = reward_hopper(M, link_origin_w(M, 0, s));
+      } else if (reward_kind == MBD_REWARD_CARTPOLE) {
+        r = reward_cartpole(M, s, S.xq(1));   // link 1 published its rotation before the end-of-substep barrier
       } else {
         r = reward_post(reward_kind, link_origin_w(M, 0, s));
       }
@@ -1121,7 +1130,7 @@ int mbd_set_group_stagger(int cycles) {
 int mbd_layout_info(int32_t* out, int n) {
   const int32_t v[] = {(int32_t)MBD_MODEL_MAGIC, MBD_HDR_WORDS, MBD_NFIELDS, MBD_MAXL, MBD_MAXCHILD, MBD_MAXDOF, MBD_MAXCON,
                        MBD_MAXTRACK, MBD_DOF_STRIDE, MBD_CON_STRIDE, MBD_H_DT, MBD_H_RW0, MBD_F_MASS, MBD_F_COM, MBD_F_RC,
-                       MBD_F_JQ, MBD_F_RP, MBD_F_PQ, MBD_F_PARITY, MBD_F_DOF0, MBD_F_NCON, MBD_F_CON0, MBD_BLOB_WORDS,
+                       MBD_F_JQ, MBD_F_RP, MBD_F_PQ, MBD_F_PARITY, MBD_F_SLIDE, MBD_F_DOF0, MBD_F_NCON, MBD_F_CON0, MBD_BLOB_WORDS,
                        MBD_STATE_STRIDE};
   const int cnt = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < cnt && i < n; ++i) out[i] = v[i];

@@ -195,6 +195,12 @@ __device__ __forceinline__ void axis_angle_ang(q4 j, float parity, JointAngles& 
   o.ax[2] = V3(parity * r02, parity * r12, parity * r22);
 }
 
+// slide (prismatic) dof axis k of a link in world coordinates — oracle/mbd_oracle.c::slide_axis
+__device__ __forceinline__ v3 slide_axis(int k, float parity, q4 a_p) {
+  v3 e = k == 0 ? V3(1.0f, 0.0f, 0.0f) : (k == 1 ? V3(0.0f, 1.0f, 0.0f) : V3(0.0f, 0.0f, parity));
+  return vrotate(e, a_p);
+}
+
 // Per-lane constants that stay in registers for the whole rollout.
 struct LaneCfg {
   int l;         // link id (lane within the group)
@@ -203,7 +209,7 @@ struct LaneCfg {
   int psrc;      // warp lane of the parent (own lane when parent is the world)
   int has_parent;
   int csrc[MBD_MAXCHILD];  // warp lanes of the children, -1 = none
-  int ncon;
+  int ncon, smask;
   float inv_mass, pinv_mass, pinv_inertia, parity, ang_damp;
   q4 pq, jq;
   v3 rp, rc;
@@ -225,6 +231,7 @@ __device__ __forceinline__ void load_lane_cfg(const ModelSmem& M, int lane_in_wa
     c.csrc[k] = ch >= 0 ? c.gbase + ch : -1;
   }
   c.ncon = live ? M.li(MBD_F_NCON, l) : 0;
+  c.smask = (live && c.ndof > 0) ? M.li(MBD_F_SLIDE, l) : 0;
   c.inv_mass = M.lf(MBD_F_INV_MASS, l);
   c.pinv_mass = M.lf(MBD_F_PINV_MASS, l);
   c.pinv_inertia = M.lf(MBD_F_PINV_INERTIA, l);
@@ -261,6 +268,7 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
 
   // ---- joints.acceleration_update ----------------------------------------------------------
   v3 T = V3(0.0f, 0.0f, 0.0f);
+  v3 Fa = V3(0.0f, 0.0f, 0.0f);   // linear acceleration from slide-dof forces
   if (jointed) {
     q4 a_p = qmul(qp, c.pq);
     q4 a_c = qmul(s.q, c.jq);
@@ -269,16 +277,33 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     JointAngles ja;
     axis_angle_ang(j, c.parity, ja);
     v3 tq = vscale(jd, -c.ang_damp);
+    v3 rcw_s = V3(0.0f, 0.0f, 0.0f), d_s = rcw_s, va_s = rcw_s, Fw = rcw_s;
+    if (c.smask != 0) {
+      rcw_s = vrotate(c.rc, s.q);
+      d_s = vsub(vadd(s.p, rcw_s), c.rp);
+      va_s = vadd(s.v, vcross(s.w, rcw_s));
+    }
 #pragma unroll
     for (int k = 0; k < MBD_MAXDOF; ++k) {
       if (k < c.ndof) {
         int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
-        float vel = vdot(ja.ax[k], jd);
-        float t = fmaf(-M.lf(base + MBD_D_DAMP, c.l), vel, fmaf(-M.lf(base + MBD_D_STIFF, c.l), ja.ang[k], tau[k]));
-        tq = vfma(ja.ax[k], t, tq);
+        if ((c.smask >> k) & 1) {
+          v3 ak = slide_axis(k, c.parity, a_p);
+          float x = vdot(d_s, ak), xd = vdot(va_s, ak);
+          float f = fmaf(-M.lf(base + MBD_D_DAMP, c.l), xd, fmaf(-M.lf(base + MBD_D_STIFF, c.l), x, tau[k]));
+          Fw = vfma(ak, f, Fw);
+        } else {
+          float vel = vdot(ja.ax[k], jd);
+          float t = fmaf(-M.lf(base + MBD_D_DAMP, c.l), vel, fmaf(-M.lf(base + MBD_D_STIFF, c.l), ja.ang[k], tau[k]));
+          tq = vfma(ja.ax[k], t, tq);
+        }
       }
     }
     T = vrotate(tq, a_p);
+    if (c.smask != 0) {
+      Fa = vscale(Fw, c.inv_mass);
+      T = vadd(T, vcross(rcw_s, Fw));
+    }
   }
   // gather: acc = T_own - sum_children T_child (ascending child order)
   v3 acc = T;
@@ -290,7 +315,8 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
   }
   // ---- integrator.integrate_xdd ---------------------------------------------------------------
   s.w = V3(fmaf(acc.x, K.dt, s.w.x * K.ang_damp), fmaf(acc.y, K.dt, s.w.y * K.ang_damp), fmaf(acc.z, K.dt, s.w.z * K.ang_damp));
-  s.v = V3(fmaf(K.g.x, K.dt, s.v.x * K.vel_damp), fmaf(K.g.y, K.dt, s.v.y * K.vel_damp), fmaf(K.g.z, K.dt, s.v.z * K.vel_damp));
+  const v3 al = vadd(K.g, Fa);   // g + 0 == g bit for bit on links without slide dofs
+  s.v = V3(fmaf(al.x, K.dt, s.v.x * K.vel_damp), fmaf(al.y, K.dt, s.v.y * K.vel_damp), fmaf(al.z, K.dt, s.v.z * K.vel_damp));
   s.q = qnormalize(qadd(s.q, vqmul(vscale(s.w, K.half_dt), s.q)));
   s.p = vfma(s.v, K.dt, s.p);
   const v3 w_before = s.w, v_before = s.v;  // xd_i right after integration
@@ -306,6 +332,17 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     v3 rpw = vrotate(c.rp, qp);
     v3 rcw = vrotate(c.rc, s.q);
     v3 e = vsub(vadd(s.p, rcw), vadd(pp, rpw));
+    q4 a_p = qmul(qp, c.pq);
+    if (c.smask != 0) {
+#pragma unroll
+      for (int k = 0; k < MBD_MAXDOF; ++k)
+        if (k < c.ndof && ((c.smask >> k) & 1)) {
+          int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+          v3 ak = slide_axis(k, c.parity, a_p);
+          float x = vdot(e, ak);
+          e = vfma(ak, -clampf(x, M.lf(base + MBD_D_LO, c.l), M.lf(base + MBD_D_HI, c.l)), e);
+        }
+    }
     float cn;
     v3 n = vnormalize(e, &cn);
     v3 crc = vcross(rcw, n), crp = vcross(rpw, n);
@@ -318,15 +355,14 @@ __device__ __forceinline__ void positional_step(const ModelSmem& M, const LaneCf
     q4 dq_c = vqmul(vcross(rcw, P), s.q);
     v3 dp_p = vscale(P, -im_p);
     q4 dq_p = vqmul(vcross(rpw, P), qp);
-    q4 a_p = qmul(qp, c.pq);
     q4 a_c = qmul(s.q, c.jq);
     q4 j = qmul(qconj(a_p), a_c);
     JointAngles ja;
     axis_angle_ang(j, c.parity, ja);
     const int b0 = MBD_F_DOF0, b1 = MBD_F_DOF0 + MBD_DOF_STRIDE, b2 = MBD_F_DOF0 + 2 * MBD_DOF_STRIDE;
-    float e0 = ja.ang[0] - clampf(ja.ang[0], M.lf(b0 + MBD_D_LO, c.l), M.lf(b0 + MBD_D_HI, c.l));
-    float e1 = ja.ang[1] - clampf(ja.ang[1], M.lf(b1 + MBD_D_LO, c.l), M.lf(b1 + MBD_D_HI, c.l));
-    float e2 = ja.ang[2] - clampf(ja.ang[2], M.lf(b2 + MBD_D_LO, c.l), M.lf(b2 + MBD_D_HI, c.l));
+    float e0 = (c.smask & 1) ? ja.ang[0] : ja.ang[0] - clampf(ja.ang[0], M.lf(b0 + MBD_D_LO, c.l), M.lf(b0 + MBD_D_HI, c.l));
+    float e1 = (c.smask & 2) ? ja.ang[1] : ja.ang[1] - clampf(ja.ang[1], M.lf(b1 + MBD_D_LO, c.l), M.lf(b1 + MBD_D_HI, c.l));
+    float e2 = (c.smask & 4) ? ja.ang[2] : ja.ang[2] - clampf(ja.ang[2], M.lf(b2 + MBD_D_LO, c.l), M.lf(b2 + MBD_D_HI, c.l));
     v3 dqj_n = vscale(ja.ax[0], e0);
     dqj_n = vfma(ja.ax[1], e1, dqj_n);
     dqj_n = vfma(ja.ax[2], e2, dqj_n);
@@ -403,7 +439,22 @@ __device__ __forceinline__ float reward_post(int kind, v3 x0) {
   }
   if (kind == MBD_REWARD_HUMANOIDSTANDUP)  // humanoidstandup.py:50-56
     return ((1.5f - clampf(fabsf(x0.z - 1.3f), -2.0f, 1.0f)) - fabsf(x0.x) * 0.1f) - fabsf(x0.y) * 0.1f;
-  return x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;  // hopper.py:57-65
+  return x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;  // hopper.py:57-65 (callers pass kinds with parameters to the functions below)
+}
+// hopper.py:57-65 (z0 = 1.0) / walker2d.py:56-61 (z0 = 1.1)
+__device__ __forceinline__ float reward_hopper(const ModelSmem& M, v3 x0) {
+  return x0.x - clampf(fabsf(x0.z - M.hf(MBD_H_RW0)), -1.0f, 1.0f) * 0.5f;
+}
+// cartpole.py:44 — oracle/mbd_oracle.c::reward_post(MBD_REWARD_CARTPOLE): cart = link 0 (state of the caller), q1 = rotation of link 1
+__device__ __forceinline__ float reward_cartpole(const ModelSmem& M, const LinkState& cart, q4 q1) {
+  q4 a_p = qmul(cart.q, M.l4(MBD_F_PQ, 1));
+  q4 a_c = qmul(q1, M.l4(MBD_F_JQ, 1));
+  JointAngles ja;
+  axis_angle_ang(qmul(qconj(a_p), a_c), M.lf(MBD_F_PARITY, 1), ja);
+  v3 rcw = vrotate(M.l3(MBD_F_RC, 0), cart.q);
+  v3 va = vadd(cart.v, vcross(cart.w, rcw));
+  float xd = vdot(va, slide_axis(0, M.lf(MBD_F_PARITY, 0), M.l4(MBD_F_PQ, 0)));
+  return mbd_cosf(ja.ang[0]) - fabsf(xd);
 }
 
 // brax/envs/ant.py reward (oracle/mbd_oracle.c::reward_ant): forward velocity of the root + healthy reward - control cost;

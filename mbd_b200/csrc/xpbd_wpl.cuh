@@ -62,7 +62,7 @@ struct WplSmem {
 // from the shared-memory model table where they are used (broadcast LDS) — caching them cost ~40
 // registers per thread and forced spills under the 2-CTAs/SM register cap.
 struct WarpCfg {
-  int l, ndof, parent, ncon;
+  int l, ndof, parent, ncon, smask;   // smask: bit k = dof k is a slide dof (world-parented links only)
   int child[MBD_MAXCHILD];
 };
 
@@ -71,6 +71,7 @@ __device__ __forceinline__ void load_warp_cfg(const ModelSmem& M, int l, WarpCfg
   c.ndof = M.li(MBD_F_NDOF, l);
   c.parent = M.li(MBD_F_PARENT, l);
   c.ncon = M.li(MBD_F_NCON, l);
+  c.smask = c.ndof > 0 ? M.li(MBD_F_SLIDE, l) : 0;
 #pragma unroll
   for (int k = 0; k < MBD_MAXCHILD; ++k) c.child[k] = M.li(MBD_F_CHILD0 + k, l);
 }
@@ -294,8 +295,42 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
 
   // ---- A: joints.acceleration_update ----------------------------------------------------------
   v3 T = V3(0.0f, 0.0f, 0.0f);
+  v3 Fa = V3(0.0f, 0.0f, 0.0f);   // linear acceleration from slide-dof forces (links with slide dofs only)
   Y.wait_pose(jointed ? c.parent : -1);
-  if (jointed) {
+  if (jointed && c.smask != 0) {
+    // links with slide dofs (planar roots, the cartpole cart; parent = world): oracle/mbd_oracle.c, "slide dofs"
+    q4 a_p = qmul(Q4(1.0f, 0.0f, 0.0f, 0.0f), M.l4(MBD_F_PQ, c.l));
+    q4 a_c = qmul(s.q, M.l4(MBD_F_JQ, c.l));
+    q4 j = qmul(qconj(a_p), a_c);
+    v3 jd = vinv_rotate(vsub(s.w, V3(0.0f, 0.0f, 0.0f)), a_p);
+    v3 tq = vscale(jd, -M.lf(MBD_F_ANG_DAMP, c.l));
+    JointAngles ja;
+    axis_angle_ang(j, M.lf(MBD_F_PARITY, c.l), ja);
+    v3 rcw = vrotate(M.l3(MBD_F_RC, c.l), s.q);
+    v3 d = vsub(vadd(s.p, rcw), M.l3(MBD_F_RP, c.l));
+    v3 va = vadd(s.v, vcross(s.w, rcw));
+    v3 Fw = V3(0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < MBD_MAXDOF; ++k) {
+      if (k < c.ndof) {
+        int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+        if ((c.smask >> k) & 1) {
+          v3 ak = slide_axis(k, M.lf(MBD_F_PARITY, c.l), a_p);
+          float x = vdot(d, ak), xd = vdot(va, ak);
+          float f = fmaf(-M.lf(base + MBD_D_DAMP, c.l), xd, fmaf(-M.lf(base + MBD_D_STIFF, c.l), x, tau[k]));
+          Fw = vfma(ak, f, Fw);
+        } else {
+          float vel = vdot(ja.ax[k], jd);
+          float t = fmaf(-M.lf(base + MBD_D_DAMP, c.l), vel, fmaf(-M.lf(base + MBD_D_STIFF, c.l), ja.ang[k], tau[k]));
+          tq = vfma(ja.ax[k], t, tq);
+        }
+      }
+    }
+    T = vrotate(tq, a_p);
+    Fa = vscale(Fw, M.lf(MBD_F_INV_MASS, c.l));
+    T = vadd(T, vcross(rcw, Fw));
+    S.put_e3(c.l, 0, T);
+  } else if (jointed) {
     q4 qp = Q4(1.0f, 0.0f, 0.0f, 0.0f);
     v3 wp = V3(0.0f, 0.0f, 0.0f);
     if (has_parent) { qp = S.xq(c.parent); wp = S.xw(c.parent); }
@@ -338,7 +373,9 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     for (int k = 0; k < MBD_MAXCHILD; ++k)
       if (c.child[k] >= 0) acc = vsub(acc, S.e3(c.child[k], 0));
     s.w = V3(fmaf(acc.x, M.hf(MBD_H_DT), s.w.x * M.hf(MBD_H_ANG_DAMP)), fmaf(acc.y, M.hf(MBD_H_DT), s.w.y * M.hf(MBD_H_ANG_DAMP)), fmaf(acc.z, M.hf(MBD_H_DT), s.w.z * M.hf(MBD_H_ANG_DAMP)));
-    s.v = V3(fmaf(M.hf(MBD_H_GX), M.hf(MBD_H_DT), s.v.x * M.hf(MBD_H_VEL_DAMP)), fmaf(M.hf(MBD_H_GY), M.hf(MBD_H_DT), s.v.y * M.hf(MBD_H_VEL_DAMP)), fmaf(M.hf(MBD_H_GZ), M.hf(MBD_H_DT), s.v.z * M.hf(MBD_H_VEL_DAMP)));
+    v3 al = V3(M.hf(MBD_H_GX), M.hf(MBD_H_GY), M.hf(MBD_H_GZ));
+    if (c.smask != 0) al = vadd(al, Fa);   // warp-uniform; g + 0 == g bit for bit, so the oracle adds unconditionally
+    s.v = V3(fmaf(al.x, M.hf(MBD_H_DT), s.v.x * M.hf(MBD_H_VEL_DAMP)), fmaf(al.y, M.hf(MBD_H_DT), s.v.y * M.hf(MBD_H_VEL_DAMP)), fmaf(al.z, M.hf(MBD_H_DT), s.v.z * M.hf(MBD_H_VEL_DAMP)));
     s.q = qnormalize(qadd(s.q, vqmul(vscale(s.w, M.hf(MBD_H_HALF_DT)), s.q)));
     s.p = vfma(s.v, M.hf(MBD_H_DT), s.p);
     S.put_p(c.l, s.p);
@@ -361,6 +398,17 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     v3 rpw = vrotate(M.l3(MBD_F_RP, c.l), qp);
     v3 rcw = vrotate(M.l3(MBD_F_RC, c.l), s.q);
     v3 e = vsub(vadd(s.p, rcw), vadd(pp, rpw));
+    q4 a_p = qmul(qp, M.l4(MBD_F_PQ, c.l));
+    if (c.smask != 0) {   // prismatic dofs: what the limits allow along each slide axis is not an error
+#pragma unroll
+      for (int k = 0; k < MBD_MAXDOF; ++k)
+        if (k < c.ndof && ((c.smask >> k) & 1)) {
+          int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+          v3 ak = slide_axis(k, M.lf(MBD_F_PARITY, c.l), a_p);
+          float x = vdot(e, ak);
+          e = vfma(ak, -clampf(x, M.lf(base + MBD_D_LO, c.l), M.lf(base + MBD_D_HI, c.l)), e);
+        }
+    }
     float cn;
     v3 n = vnormalize(e, &cn);
     v3 crc = vcross(rcw, n), crp = vcross(rpw, n);
@@ -373,7 +421,6 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     q4 dq_c = vqmul(vcross(rcw, P), s.q);
     v3 dp_p = vscale(P, -im_p);
     q4 dq_p = vqmul(vcross(rpw, P), qp);
-    q4 a_p = qmul(qp, M.l4(MBD_F_PQ, c.l));
     q4 a_c = qmul(s.q, M.l4(MBD_F_JQ, c.l));
     q4 j = qmul(qconj(a_p), a_c);
     v3 dqj;
@@ -381,14 +428,14 @@ __device__ __forceinline__ void positional_step_wpl(const ModelSmem& M, const Wa
     if (c.ndof == 1) {
       float psi, r10, r20;
       axis_angle_1dof(j, psi, r10, r20);
-      float e0 = psi - clampf(psi, M.lf(b0 + MBD_D_LO, c.l), M.lf(b0 + MBD_D_HI, c.l));
+      float e0 = (c.smask & 1) ? psi : psi - clampf(psi, M.lf(b0 + MBD_D_LO, c.l), M.lf(b0 + MBD_D_HI, c.l));
       dqj = V3(e0, -r20, r10);
     } else {
       JointAngles ja;
       axis_angle_ang(j, M.lf(MBD_F_PARITY, c.l), ja);
-      float e0 = ja.ang[0] - clampf(ja.ang[0], M.lf(b0 + MBD_D_LO, c.l), M.lf(b0 + MBD_D_HI, c.l));
-      float e1 = ja.ang[1] - clampf(ja.ang[1], M.lf(b1 + MBD_D_LO, c.l), M.lf(b1 + MBD_D_HI, c.l));
-      float e2 = ja.ang[2] - clampf(ja.ang[2], M.lf(b2 + MBD_D_LO, c.l), M.lf(b2 + MBD_D_HI, c.l));
+      float e0 = (c.smask & 1) ? ja.ang[0] : ja.ang[0] - clampf(ja.ang[0], M.lf(b0 + MBD_D_LO, c.l), M.lf(b0 + MBD_D_HI, c.l));
+      float e1 = (c.smask & 2) ? ja.ang[1] : ja.ang[1] - clampf(ja.ang[1], M.lf(b1 + MBD_D_LO, c.l), M.lf(b1 + MBD_D_HI, c.l));
+      float e2 = (c.smask & 4) ? ja.ang[2] : ja.ang[2] - clampf(ja.ang[2], M.lf(b2 + MBD_D_LO, c.l), M.lf(b2 + MBD_D_HI, c.l));
       dqj = vscale(ja.ax[0], e0);
       dqj = vfma(ja.ax[1], e1, dqj);
       dqj = vfma(ja.ax[2], e2, dqj);

@@ -1,6 +1,7 @@
 """Ant — Brax's stock `ant` as the reference instantiates it (`brax_envs.get_environment("ant", backend="positional")`,
 /root/reference/mbd/envs/__init__.py:30-31).  Neither the env nor its MJCF is part of the reference tree: the env below
-restates brax/envs/ant.py **[brax-recalled]** and the MJCF is looked up in the user's Brax install (or `MBD_BRAX_ASSETS`).
+restates brax/envs/ant.py **[brax-recalled]**; the MJCF comes from `brax_asset` (a Brax install, `MBD_BRAX_ASSETS`, or this
+repo's restatement of the public Gym model, mbd_b200/assets/ant.xml).
 
 Restated behaviour: positional backend => `opt.timestep = 0.005`, `n_frames = 10` (env dt 0.05), every actuator gear 200;
 reset: `q = init_q + U(-0.1, 0.1)`, `qd = 0.1 * N(0, 1)`; reward = forward velocity of the torso
@@ -8,33 +9,13 @@ reset: `q = init_q + U(-0.1, 0.1)`, `qd = 0.1 * N(0, 1)`; reward = forward veloc
 cost off; termination does not stop a planner rollout (`rollout_us` never resets)."""
 from __future__ import annotations
 
-import importlib.util
-import os
-
 import numpy as np
 import torch
 
 from .. import ops, prng
 from ..model import blob as blob_mod
 from ..model import mjcf
-from .base import PipelineEnv, PipelineState, State
-
-
-def find_brax_asset(name: str) -> str | None:
-    """`<MBD_BRAX_ASSETS>/<name>` or `<site-packages>/brax/envs/assets/<name>`; None when neither exists."""
-    cands = []
-    if os.environ.get("MBD_BRAX_ASSETS"):
-        cands.append(os.path.join(os.environ["MBD_BRAX_ASSETS"], name))
-    try:
-        spec = importlib.util.find_spec("brax")
-    except (ImportError, ValueError):
-        spec = None
-    if spec is not None and spec.submodule_search_locations:
-        cands.append(os.path.join(list(spec.submodule_search_locations)[0], "envs", "assets", name))
-    for c in cands:
-        if os.path.exists(c):
-            return c
-    return None
+from .base import PipelineEnv, PipelineState, State, brax_asset
 
 
 class Ant(PipelineEnv):
@@ -42,12 +23,7 @@ class Ant(PipelineEnv):
 
     def __init__(self, xml_path: str | None = None, ctrl_cost_weight: float = 0.5, healthy_reward: float = 1.0,
                  reset_noise_scale: float = 0.1):
-        path = xml_path or find_brax_asset("ant.xml")
-        if path is None:
-            raise NotImplementedError("environment 'ant' needs Brax's ant.xml: it lives inside the Brax wheel "
-                                      "(brax/envs/assets/ant.xml), not in the reference tree — install Brax, set "
-                                      "MBD_BRAX_ASSETS to a directory that holds it, or pass xml_path")
-        sys = mjcf.load(path)
+        sys = mjcf.load(xml_path or brax_asset("ant.xml"))
         sys.dt = 0.005                                   # ant.py: positional => opt.timestep 0.005, n_frames 10
         sys.act_gear = np.full_like(sys.act_gear, 200.0)  # ant.py: positional => gear 200 on every actuator
         self._reset_noise_scale = float(reset_noise_scale)

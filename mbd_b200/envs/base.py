@@ -29,6 +29,28 @@ def load_system(name: str) -> mjcf.System:
     return mjcf.load(os.path.join(ref, name + ".xml"))
 
 
+def brax_asset(name: str) -> str:
+    """Path of an MJCF the reference takes from INSIDE the Brax wheel (`epath.resource_path("brax") /
+    "envs/assets/<name>"`, /root/reference/mbd/envs/hopper.py:13, walker2d.py:14; ant / halfcheetah through
+    `brax.envs`).  Lookup order: `$MBD_BRAX_ASSETS/<name>`, an installed Brax, then this repo's own restatement
+    of the public model under mbd_b200/assets/ (provenance in each file's header; unpinned like all Brax behaviour)."""
+    import importlib.util
+    cands = []
+    if os.environ.get("MBD_BRAX_ASSETS"):
+        cands.append(os.path.join(os.environ["MBD_BRAX_ASSETS"], name))
+    try:
+        spec = importlib.util.find_spec("brax")
+    except (ImportError, ValueError):
+        spec = None
+    if spec is not None and spec.submodule_search_locations:
+        cands.append(os.path.join(list(spec.submodule_search_locations)[0], "envs", "assets", name))
+    cands.append(os.path.join(ASSET_DIR, name))
+    for c in cands:
+        if os.path.exists(c):
+            return c
+    raise FileNotFoundError(name)
+
+
 @dataclasses.dataclass
 class Transform:
     pos: np.ndarray

@@ -29,7 +29,8 @@ F_RP = F_JQ + 4
 F_PQ = F_RP + 3
 F_PARITY = F_PQ + 4
 F_ANG_DAMP = F_PARITY + 1
-F_DOF0 = F_ANG_DAMP + 1
+F_SLIDE = F_ANG_DAMP + 1
+F_DOF0 = F_SLIDE + 1
 F_NCON = F_DOF0 + MAXDOF * DOF_STRIDE
 F_CON0 = F_NCON + 1
 NFIELDS = F_CON0 + MAXCON * CON_STRIDE
@@ -37,7 +38,7 @@ D_STIFF, D_DAMP, D_LO, D_HI, D_ACT, D_GEAR, D_CLO, D_CHI = range(8)
 BLOB_WORDS = HDR_WORDS + NFIELDS * MAXL
 STATE_STRIDE = 13
 
-REWARD_HUMANOIDRUN, REWARD_HUMANOIDTRACK, REWARD_HOPPER, REWARD_HUMANOIDSTANDUP, REWARD_ANT = 0, 1, 2, 3, 4
+REWARD_HUMANOIDRUN, REWARD_HUMANOIDTRACK, REWARD_HOPPER, REWARD_HUMANOIDSTANDUP, REWARD_ANT, REWARD_CARTPOLE = 0, 1, 2, 3, 4, 5
 
 _BIG = 3.0e38  # stands in for +-inf limits (keeps the arithmetic NaN-free)
 
@@ -45,7 +46,7 @@ _BIG = 3.0e38  # stands in for +-inf limits (keeps the arithmetic NaN-free)
 def layout_words():
     """The numbers `mbd_layout_info` must return (ABI cross-check)."""
     return [MAGIC, HDR_WORDS, NFIELDS, MAXL, MAXCHILD, MAXDOF, MAXCON, MAXTRACK, DOF_STRIDE, CON_STRIDE,
-            H_DT, H_RW0, F_MASS, F_COM, F_RC, F_JQ, F_RP, F_PQ, F_PARITY, F_DOF0, F_NCON, F_CON0,
+            H_DT, H_RW0, F_MASS, F_COM, F_RC, F_JQ, F_RP, F_PQ, F_PARITY, F_SLIDE, F_DOF0, F_NCON, F_CON0,
             BLOB_WORDS, STATE_STRIDE]
 
 
@@ -98,8 +99,15 @@ def pack(sys: System, n_frames: int, reward: int, links=None, track_links=(), re
 
     act_of_dof = {int(q): a for a, q in enumerate(sys.act_qd_id)}
     for old in links:
-        if np.any(sys.dof_is_slide[sys.dof_link == old]):
-            raise NotImplementedError("slide joints are outside the simulated subset")
+        sl = sys.dof_is_slide[sys.dof_link == old]
+        if np.any(sl):
+            # slide dofs: planar roots (hopper / walker2d / halfcheetah) and the cartpole cart — always on a link whose
+            # parent is the world, and always BEFORE the hinges of the same link (the slide axes then live in the fixed
+            # parent-side joint frame); that is the only arrangement the step implements
+            if sys.link_parents[old] >= 0:
+                raise NotImplementedError("slide joints are only supported on links whose parent is the world")
+            if np.any(np.diff(sl.astype(int)) > 0):
+                raise NotImplementedError("slide joints must precede the hinge joints of their link")
     for new, old in enumerate(links):
         par_old = sys.link_parents[old]
         if par_old >= 0 and par_old not in remap:
@@ -124,6 +132,8 @@ def pack(sys: System, n_frames: int, reward: int, links=None, track_links=(), re
         f[lf(F_ANG_DAMP, new)] = sys.custom["constraint_ang_damping"]
         f[lf(F_PARITY, new)] = sys.joint_parity[old]
         if ndof > 0:
+            d0_ = int(sys.link_dof_start[old])
+            i32[lf(F_SLIDE, new)] = sum(1 << k for k in range(ndof) if sys.dof_is_slide[d0_ + k])
             rc = sys.joint_pos[old] - com
             jq = sys.joint_rot[old]
             # parent side: link.transform.do(link.joint), lever arm from the parent's COM

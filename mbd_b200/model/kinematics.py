@@ -44,11 +44,11 @@ def forward(sys: System, q: np.ndarray, qd: np.ndarray):
         for k in range(nd):
             axis = sys.dof_axis[ds + k]
             if sys.dof_is_slide[ds + k]:  # prismatic dof: translation along the axis (link-transform frame)
-                slide_pos = slide_pos + rotate(axis * q[qs + k], jrot)
+                slide_pos = slide_pos + rotate(axis * (q[qs + k] - sys.ref(ds + k)), jrot)
                 slide_vel = slide_vel + rotate(axis * qd[ds + k], jrot)
                 continue
             jang = jang + rotate(axis * qd[ds + k], jrot)
-            jrot = quat_mul(jrot, _quat_rot_axis(axis, q[qs + k]))
+            jrot = quat_mul(jrot, _quat_rot_axis(axis, q[qs + k] - sys.ref(ds + k)))
         jp = sys.joint_pos[l]
         jpos = jp - rotate(jp, jrot) + slide_pos  # rotation about the joint anchor (+ slide offset)
         ppos = xpos[par] if par >= 0 else np.zeros(3)
@@ -124,7 +124,19 @@ def inverse(sys: System, xpos, xrot, xang, xvel, links=None):
         lon = lon / (np.linalg.norm(lon) + 1e-30)
         axes = [np.array([1.0, 0, 0]), lon, par_sign * np.array([r02, r12, r22])]
         jd = rotate(xang[l] - pang, a_p * np.array([1.0, -1, -1, -1]))
+        # slide dofs (world-parented links only, blob.pack enforces it): coordinate along the fixed parent-side axis
+        trot = quat_mul(prot, sys.link_rot[l])
+        ppos = xpos[par] if par >= 0 else np.zeros(3)
+        anchor_p = ppos + rotate(sys.link_pos[l] + rotate(sys.joint_pos[l], sys.link_rot[l]), prot)
+        rcw = rotate(sys.joint_pos[l], xrot[l])
+        d = xpos[l] + rcw - anchor_p
+        v_anchor = xvel[l] + np.cross(xang[l], rcw)
         for k in range(nd):
-            q[qs + k] = ang[k]
+            if sys.dof_is_slide[ds + k]:
+                axis_w = rotate(sys.dof_axis[ds + k], trot)
+                q[qs + k] = sys.ref(ds + k) + float(np.dot(d, axis_w))
+                qd[ds + k] = float(np.dot(v_anchor, axis_w))
+                continue
+            q[qs + k] = ang[k] + sys.ref(ds + k)
             qd[ds + k] = float(np.dot(axes[k], jd))
     return q.astype(np.float32), qd.astype(np.float32)

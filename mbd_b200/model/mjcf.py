@@ -120,6 +120,7 @@ class Joint:
     stiffness: float
     damping: float
     armature: float
+    ref: float = 0.0  # MuJoCo `ref`: the joint coordinate of the pose written in the XML (qpos0)
 
 
 @dataclasses.dataclass
@@ -177,6 +178,10 @@ class System:
     gravity: np.ndarray
     init_q: np.ndarray
     custom: Dict[str, float]
+    dof_ref: Optional[np.ndarray] = None  # [nv] MuJoCo `ref` per 1-dof joint (zeros when absent): displacement = q - ref
+
+    def ref(self, d: int) -> float:
+        return 0.0 if self.dof_ref is None else float(self.dof_ref[d])
 
     # Brax-compatible accessors used by the reference envs ---------------------------
     def q_size(self) -> int:
@@ -278,13 +283,18 @@ def _geom_mass_inertia(g: Geom):
     return m, i
 
 
-def _parse_geom(elem, defaults, active_class) -> Geom:
+def _parse_geom(elem, defaults, active_class, degree: bool = True) -> Geom:
     a = defaults.resolve(elem, "geom", active_class)
     typ = a.get("type", "sphere")
     size = _vec(a.get("size"), [0.0])
     pos = _vec(a.get("pos"), [0, 0, 0])
     quat = _vec(a.get("quat"), [1, 0, 0, 0])
     quat = quat / np.linalg.norm(quat)
+    if "axisangle" in a:  # MuJoCo axisangle="x y z angle" (angle in the compiler's unit)
+        aa = _vec(a["axisangle"], None)
+        ang = np.deg2rad(aa[3]) if degree else aa[3]
+        ax = aa[:3] / np.linalg.norm(aa[:3])
+        quat = np.concatenate([[np.cos(ang / 2)], ax * np.sin(ang / 2)])
     if typ == "capsule":
         if "fromto" in a:
             pos, quat, half = _capsule_frame_from_fromto(_vec(a["fromto"], None))
@@ -321,6 +331,7 @@ def _parse_joint(elem, defaults, active_class, degree: bool) -> Joint:
         name=a.get("name", ""), type=typ, pos=_vec(a.get("pos"), [0, 0, 0]), axis=axis, range=rng,
         stiffness=float(a.get("stiffness", 0.0)), damping=float(a.get("damping", 0.0)),
         armature=float(a.get("armature", 0.0)),
+        ref=(np.deg2rad(float(a.get("ref", 0.0))) if (typ == "hinge" and degree) else float(a.get("ref", 0.0))),
     )
 
 
@@ -328,7 +339,7 @@ def _collect_bodies(elem, parent, defaults, active_class, degree, out: List[Body
     """Depth-first walk.  Joint-less bodies are fused into their parent (Brax `_fuse_bodies`)."""
     for child in elem:
         if child.tag == "geom" and parent == -1:
-            g = _parse_geom(child, defaults, active_class)
+            g = _parse_geom(child, defaults, active_class, degree)
             g.body = -1
             world_geoms.append(g)
     for b in elem.findall("body"):
@@ -339,7 +350,7 @@ def _collect_bodies(elem, parent, defaults, active_class, degree, out: List[Body
         joints = [_parse_joint(j, defaults, cls, degree) for j in b.findall("joint")]
         if b.find("freejoint") is not None:
             joints = [Joint("root", "free", np.zeros(3), np.array([0, 0, 1.0]), np.array([-np.inf, np.inf]), 0, 0, 0)]
-        geoms = [_parse_geom(g, defaults, cls) for g in b.findall("geom")]
+        geoms = [_parse_geom(g, defaults, cls, degree) for g in b.findall("geom")]
         if not joints and parent >= 0:
             # fuse into parent: re-express geoms (and the subtree) in the parent's frame
             for g in geoms:
@@ -396,7 +407,7 @@ def load(path: str) -> System:
     link_pos = np.zeros((L, 3)); link_rot = np.tile([1.0, 0, 0, 0], (L, 1))
     joint_pos = np.zeros((L, 3)); joint_rot = np.tile([1.0, 0, 0, 0], (L, 1)); parity = np.ones(L)
     mass = np.zeros(L); com = np.zeros((L, 3)); inertia = np.zeros((L, 3, 3))
-    dof_link, dof_axis, dof_slide, dof_k, dof_d, dof_arm, dof_lim = [], [], [], [], [], [], []
+    dof_link, dof_axis, dof_slide, dof_k, dof_d, dof_arm, dof_lim, dof_ref = [], [], [], [], [], [], [], []
     link_dof_start = np.zeros(L, dtype=np.int64); link_q_start = np.zeros(L, dtype=np.int64)
     init_q: List[float] = []
     joint_dof: Dict[str, int] = {}; joint_q: Dict[str, int] = {}
@@ -410,14 +421,15 @@ def load(path: str) -> System:
             joint_dof[b.joints[0].name] = len(dof_link); joint_q[b.joints[0].name] = link_q_start[i]
             for _ in range(6):
                 dof_link.append(i); dof_axis.append(np.zeros(3)); dof_slide.append(False)
-                dof_k.append(0.0); dof_d.append(0.0); dof_arm.append(0.0); dof_lim.append([-np.inf, np.inf])
+                dof_k.append(0.0); dof_d.append(0.0); dof_arm.append(0.0); dof_lim.append([-np.inf, np.inf]); dof_ref.append(0.0)
         else:
             link_pos[i], link_rot[i] = b.pos, b.quat
             axes = [j.axis for j in b.joints]
             joint_pos[i] = b.joints[0].pos
             for j in b.joints:
                 joint_dof[j.name] = len(dof_link); joint_q[j.name] = len(init_q)
-                init_q.append(0.0)
+                init_q.append(j.ref)   # MuJoCo qpos0 = ref
+                dof_ref.append(j.ref)
                 dof_link.append(i); dof_axis.append(j.axis); dof_slide.append(j.type == "slide")
                 dof_k.append(j.stiffness); dof_d.append(j.damping); dof_arm.append(j.armature)
                 dof_lim.append(list(j.range))
@@ -452,6 +464,11 @@ def load(path: str) -> System:
             d = g.pos - c
             it += r @ ig @ r.T + m * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
         mass[i], com[i], inertia[i] = m_tot, c, it
+
+    if compiler is not None and compiler.get("settotalmass") is not None:
+        # MuJoCo compiler settotalmass: scale every body mass (and inertia) so that the masses add up to the given value
+        k = float(compiler.get("settotalmass")) / mass.sum()
+        mass, inertia = mass * k, inertia * k
 
     # actuators (motor / general with gear; position actuators carry bias)
     act_names, act_qd, act_q, act_gear, act_ctrl, act_gain, act_bq, act_bqd = [], [], [], [], [], [], [], []
@@ -509,4 +526,5 @@ def load(path: str) -> System:
         init_q=(np.asarray(custom["init_qpos"], dtype=np.float64) if isinstance(custom.get("init_qpos"), np.ndarray)
                 and len(custom["init_qpos"]) == len(init_q) else np.array(init_q)),
         custom={k: v for k, v in custom.items() if not isinstance(v, np.ndarray)},
+        dof_ref=np.array(dof_ref),
     )

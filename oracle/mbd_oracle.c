@@ -237,6 +237,20 @@ static inline void contact_velocity_plane(const Model* m, int l, int ci, float i
   *dw = vadd(*dw, vcross(r, P));
 }
 
+/* ---- slide (prismatic) dofs -------------------------------------------------------------------------
+ * [restated] Brax's positional joints treat a translational dof like XPBD's prismatic joint (Mueller et al.
+ * 2020, sec. 3.4.2): the component of the anchor offset along the free axis is removed from the positional error
+ * (what exceeds the limits stays in), and the dof's spring / damper / motor act as a force along the axis at the
+ * child anchor.  Brax's exact expressions are unpinned like the rest of the physics; the form below is this
+ * repo's.  Supported arrangement (blob.pack enforces it): the link's parent is the WORLD and its slide dofs
+ * precede its hinges, so the slide axes are the fixed columns of the parent-side joint frame a_p = PQ —
+ * planar roots (hopper, walker2d, halfcheetah: slide x, slide z, hinge y) and the cartpole cart.
+ * Axis of dof k in the joint frame: e_k (the third column carries the parity, like the third hinge axis). */
+static inline v3 slide_axis(int k, float parity, q4 a_p) {
+  v3 e = k == 0 ? V3(1.0f, 0.0f, 0.0f) : (k == 1 ? V3(0.0f, 1.0f, 0.0f) : V3(0.0f, 0.0f, parity));
+  return vrotate(e, a_p);
+}
+
 /* ================================================================================== */
 /* brax/positional/pipeline.py: step                                                   */
 /* ================================================================================== */
@@ -244,6 +258,7 @@ static void positional_step(const Model* m, Link* s, const float* act) {
   const int L = m->L;
   Link prev[MBD_MAXL];
   v3 T[MBD_MAXL];
+  v3 Fa[MBD_MAXL]; /* linear acceleration from slide-dof forces (zero for every other link) */
   memcpy(prev, s, sizeof(Link) * L); /* x_i_prev = state.x_i */
 
   /* ---- actuator.to_tau + joints.acceleration_update -------------------------------- *
@@ -253,8 +268,10 @@ static void positional_step(const Model* m, Link* s, const float* act) {
    * (spring_inertia_scale = 1 -> identity inertia), xdd.vel = gravity.                  */
   for (int l = 0; l < L; ++l) {
     T[l] = V3(0, 0, 0);
+    Fa[l] = V3(0, 0, 0);
     int ndof = LFi(m, MBD_F_NDOF, l);
     if (ndof <= 0) continue;
+    const int smask = LFi(m, MBD_F_SLIDE, l);
     int par = LFi(m, MBD_F_PARENT, l);
     q4 qp = par >= 0 ? s[par].q : Q4(1, 0, 0, 0);
     v3 wp = par >= 0 ? s[par].w : V3(0, 0, 0);
@@ -265,17 +282,34 @@ static void positional_step(const Model* m, Link* s, const float* act) {
     JointAngles ja;
     axis_angle_ang(j, LFf(m, MBD_F_PARITY, l), &ja);
     v3 tq = vscale(jd, -LFf(m, MBD_F_ANG_DAMP, l));
+    v3 rcw_s = V3(0, 0, 0), d_s = V3(0, 0, 0), va_s = V3(0, 0, 0), Fw = V3(0, 0, 0);
+    if (smask) { /* anchor offset and anchor velocity of the child against the (fixed) world anchor RP */
+      rcw_s = vrotate(LF3(m, MBD_F_RC, l), s[l].q);
+      d_s = vsub(vadd(s[l].p, rcw_s), LF3(m, MBD_F_RP, l));
+      va_s = vadd(s[l].v, vcross(s[l].w, rcw_s));
+    }
     for (int k = 0; k < ndof; ++k) {
       int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
-      float vel = vdot(ja.ax[k], jd);
       float tau = 0.0f;
       int a_id = LFi(m, base + MBD_D_ACT, l);
       if (a_id >= 0) /* actuator.to_tau: clip(act, ctrl_range) * gear (motor: gain 1, bias 0) */
         tau = LFf(m, base + MBD_D_GEAR, l) * clampf(act[a_id], LFf(m, base + MBD_D_CLO, l), LFf(m, base + MBD_D_CHI, l));
+      if ((smask >> k) & 1) { /* slide dof: force along the axis at the child anchor */
+        v3 ak = slide_axis(k, LFf(m, MBD_F_PARITY, l), a_p);
+        float x = vdot(d_s, ak), xd = vdot(va_s, ak);
+        float f = fmaf(-LFf(m, base + MBD_D_DAMP, l), xd, fmaf(-LFf(m, base + MBD_D_STIFF, l), x, tau));
+        Fw = vfma(ak, f, Fw);
+        continue;
+      }
+      float vel = vdot(ja.ax[k], jd);
       float t = fmaf(-LFf(m, base + MBD_D_DAMP, l), vel, fmaf(-LFf(m, base + MBD_D_STIFF, l), ja.ang[k], tau));
       tq = vfma(ja.ax[k], t, tq);
     }
     T[l] = vrotate(tq, a_p);
+    if (smask) { /* F at the anchor: linear acceleration F/m, torque rcw x F about the COM (identity inertia) */
+      Fa[l] = vscale(Fw, LFf(m, MBD_F_INV_MASS, l));
+      T[l] = vadd(T[l], vcross(rcw_s, Fw));
+    }
   }
   /* ---- integrator.integrate_xdd (semi-implicit Euler) ------------------------------- */
   Link before[MBD_MAXL]; /* xd_i right after integration = "xd_i_before" for resolve_velocity */
@@ -287,7 +321,8 @@ static void positional_step(const Model* m, Link* s, const float* act) {
     }
     v3 w = s[l].w, v = s[l].v;
     w = V3(fmaf(acc.x, m->dt, w.x * m->ang_damp), fmaf(acc.y, m->dt, w.y * m->ang_damp), fmaf(acc.z, m->dt, w.z * m->ang_damp));
-    v = V3(fmaf(m->g.x, m->dt, v.x * m->vel_damp), fmaf(m->g.y, m->dt, v.y * m->vel_damp), fmaf(m->g.z, m->dt, v.z * m->vel_damp));
+    const v3 al = vadd(m->g, Fa[l]); /* g + 0 = g bit for bit on links without slide dofs */
+    v = V3(fmaf(al.x, m->dt, v.x * m->vel_damp), fmaf(al.y, m->dt, v.y * m->vel_damp), fmaf(al.z, m->dt, v.z * m->vel_damp));
     q4 q = s[l].q;
     q = qnormalize(qadd(q, vqmul(vscale(w, m->half_dt), q)));
     s[l].p = vfma(v, m->dt, s[l].p);
@@ -310,6 +345,17 @@ static void positional_step(const Model* m, Link* s, const float* act) {
     v3 rpw = vrotate(LF3(m, MBD_F_RP, l), qp);
     v3 rcw = vrotate(LF3(m, MBD_F_RC, l), s[l].q);
     v3 e = vsub(vadd(s[l].p, rcw), vadd(pp, rpw));
+    const int smask = LFi(m, MBD_F_SLIDE, l);
+    if (smask) { /* prismatic dofs: what the limits allow along each slide axis is not an error */
+      q4 a_ps = qmul(qp, LF4(m, MBD_F_PQ, l));
+      for (int k = 0; k < ndof; ++k)
+        if ((smask >> k) & 1) {
+          int base = MBD_F_DOF0 + k * MBD_DOF_STRIDE;
+          v3 ak = slide_axis(k, LFf(m, MBD_F_PARITY, l), a_ps);
+          float x = vdot(e, ak);
+          e = vfma(ak, -clampf(x, LFf(m, base + MBD_D_LO, l), LFf(m, base + MBD_D_HI, l)), e);
+        }
+    }
     float c;
     v3 n = vnormalize(e, &c);
     v3 crc = vcross(rcw, n), crp = vcross(rpw, n);
@@ -330,15 +376,16 @@ static void positional_step(const Model* m, Link* s, const float* act) {
     v3 dqj;
     {
       int b0 = MBD_F_DOF0;
-      float e0 = ja.ang[0] - clampf(ja.ang[0], LFf(m, b0 + MBD_D_LO, l), LFf(m, b0 + MBD_D_HI, l));
+      /* a slide dof leaves no rotational freedom in its slot: the whole angle is the error */
+      float e0 = (smask & 1) ? ja.ang[0] : ja.ang[0] - clampf(ja.ang[0], LFf(m, b0 + MBD_D_LO, l), LFf(m, b0 + MBD_D_HI, l));
       if (ndof == 1) {
         /* dq = cross(axis_p, axis_c) + axis * (angle - clip(angle)); in the a_p frame axis_p = e_x,
          * axis_c = first column of R(j): cross = (0, -r20, r10) */
         dqj = V3(e0, -ja.r20, ja.r10);
       } else {
         int b1 = MBD_F_DOF0 + MBD_DOF_STRIDE, b2 = MBD_F_DOF0 + 2 * MBD_DOF_STRIDE;
-        float e1 = ja.ang[1] - clampf(ja.ang[1], LFf(m, b1 + MBD_D_LO, l), LFf(m, b1 + MBD_D_HI, l));
-        float e2 = ja.ang[2] - clampf(ja.ang[2], LFf(m, b2 + MBD_D_LO, l), LFf(m, b2 + MBD_D_HI, l));
+        float e1 = (smask & 2) ? ja.ang[1] : ja.ang[1] - clampf(ja.ang[1], LFf(m, b1 + MBD_D_LO, l), LFf(m, b1 + MBD_D_HI, l));
+        float e2 = (smask & 4) ? ja.ang[2] : ja.ang[2] - clampf(ja.ang[2], LFf(m, b2 + MBD_D_LO, l), LFf(m, b2 + MBD_D_HI, l));
         dqj = vscale(ja.ax[0], e0);
         dqj = vfma(ja.ax[1], e1, dqj);
         dqj = vfma(ja.ax[2], e2, dqj);
@@ -425,8 +472,21 @@ static float reward_post(const Model* m, const Link* s) {
     return ((1.5f - clampf(fabsf(x0.z - 1.3f), -2.0f, 1.0f)) - fabsf(x0.x) * 0.1f) - fabsf(x0.y) * 0.1f;
   }
   if (m->reward == MBD_REWARD_HOPPER) {
-    /* hopper.py:57-65 */
-    return x0.x - clampf(fabsf(x0.z - 1.0f), -1.0f, 1.0f) * 0.5f;
+    /* hopper.py:57-65 (RW0 = 1.0), walker2d.py:56-61 (RW0 = 1.1) */
+    return x0.x - clampf(fabsf(x0.z - m->f[MBD_H_RW0]), -1.0f, 1.0f) * 0.5f;
+  }
+  if (m->reward == MBD_REWARD_CARTPOLE) {
+    /* cartpole.py:44: cos(q[1]) - |qd[0]|.  q[1] = hinge angle of link 1 against link 0 (kinematics.inverse: the
+     * angle psi of the joint-frame relative rotation), qd[0] = velocity of link 0's slide dof (anchor velocity
+     * along the slide axis; the world anchor is at rest) */
+    q4 a_p = qmul(s[0].q, LF4(m, MBD_F_PQ, 1));
+    q4 a_c = qmul(s[1].q, LF4(m, MBD_F_JQ, 1));
+    JointAngles ja;
+    axis_angle_ang(qmul(qconj(a_p), a_c), LFf(m, MBD_F_PARITY, 1), &ja);
+    v3 rcw = vrotate(LF3(m, MBD_F_RC, 0), s[0].q);
+    v3 va = vadd(s[0].v, vcross(s[0].w, rcw));
+    float xd = vdot(va, slide_axis(0, LFf(m, MBD_F_PARITY, 0), LF4(m, MBD_F_PQ, 0)));
+    return mbd_cosf(ja.ang[0]) - fabsf(xd);
   }
   return 0.0f;
 }

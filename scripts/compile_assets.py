@@ -3,7 +3,7 @@
 Run in the builder container (where /root/reference exists):
     python scripts/compile_assets.py [--ref /root/reference]
 Outputs (committed):
-    mbd_b200/assets/{humanoidrun,humanoidtrack,humanoidstandup}.json   compiled System (mjcf.py)
+    mbd_b200/assets/{humanoidrun,humanoidtrack,humanoidstandup,cartpole}.json   compiled System (mjcf.py)
     mbd_b200/assets/demos.npz   car2d_xref (50,2) f32; jog_xref (5,50,3) f32 built exactly as
                                 /root/reference/mbd/envs/humanoidtrack.py:33-44 does
 The pickles hold jax.Array objects; they are read with a JAX-free unpickler shim.
@@ -40,7 +40,7 @@ def main():
     src = os.path.join(a.ref, "mbd", "assets")
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "mbd_b200", "assets")
     os.makedirs(dst, exist_ok=True)
-    for name in ("humanoidrun", "humanoidtrack", "humanoidstandup"):
+    for name in ("humanoidrun", "humanoidtrack", "humanoidstandup", "cartpole"):
         s = mjcf.load(os.path.join(src, name + ".xml"))
         system_io.save(s, os.path.join(dst, name + ".json"))
         print(name, s.link_types, s.num_links(), "links")

@@ -8,8 +8,10 @@ from mbd_b200 import prng
 from mbd_b200.planners import engine as eng
 from oracle import oracle as orc
 
-CONFIGS = [("car2d", 64, 40, False, 100), ("car2d", 2048, 50, True, 100), ("humanoidrun", 8192, 50, False, 300),
-           ("humanoidtrack", 16384, 50, True, 100), ("humanoidtrack", 16384, 60, True, 100), ("humanoidstandup", 8192, 50, False, 100)]
+CONFIGS = [("car2d", 64, 40, False, 100), ("car2d", 2048, 50, True, 100), ("hopper", 1024, 50, False, 100), ("ant", 4096, 50, False, 100),
+           ("humanoidrun", 8192, 50, False, 300), ("humanoidtrack", 16384, 50, True, 100), ("humanoidtrack", 16384, 60, True, 100),
+           ("humanoidstandup", 8192, 50, False, 100), ("walker2d", 2048, 50, False, 100), ("halfcheetah", 2048, 50, False, 100),
+           ("cartpole", 2048, 50, False, 100)]
 rows = []
 for name, N, H, demo, Nd in CONFIGS:
     env = mbd_b200.envs.get_env(name)
@@ -38,7 +40,7 @@ for name, N, H, demo, Nd in CONFIGS:
     ok = np.array_equal(e.rews_local[:32].cpu().numpy().view(np.uint32), ref["rews"].view(np.uint32))
     if demo:
         ok = ok and np.array_equal(e.logpd_local[:32].cpu().numpy().view(np.uint32), ref["logpd"].view(np.uint32))
-    rows.append(dict(env=name, Nsample=N, Hsample=H, demo=demo, ms_per_step=ms, env_steps_per_s=N * H / ms * 1e3, oracle_bit_exact=bool(ok)))
+    rows.append(dict(n_frames=(env._n_frames if env.kind == 'xpbd' else 1), links=(int(env.blob.view(np.int32)[1]) if env.kind == 'xpbd' else 1), env=name, Nsample=N, Hsample=H, demo=demo, ms_per_step=ms, env_steps_per_s=N * H / ms * 1e3, oracle_bit_exact=bool(ok)))
     print(rows[-1])
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(rows, open("gpurun_out/configs_r01.json", "w"), indent=1)
+json.dump(rows, open("gpurun_out/configs_r02.json", "w"), indent=1)

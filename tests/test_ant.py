@@ -21,11 +21,11 @@ def _state(env, seed=3):
     return env.pipeline_init(q, qd).raw
 
 
-def test_registry_explains_missing_asset(monkeypatch):
+def test_registry_resolves_ant_from_the_repo_asset(monkeypatch):
+    """without a Brax install the env is built from mbd_b200/assets/ant.xml (this repo's restatement of the public model)"""
     monkeypatch.delenv("MBD_BRAX_ASSETS", raising=False)
-    if mbd_b200.envs.ant.find_brax_asset("ant.xml") is None:
-        with pytest.raises(NotImplementedError, match="ant.xml"):
-            mbd_b200.envs.get_env("ant")
+    env = mbd_b200.envs.get_env("ant")
+    assert env.sys.link_types == "f11111111" and env.action_size == 8
 
 
 def test_positional_overrides_and_reward_parameters():

@@ -48,7 +48,7 @@ def test_env_registry():
     with pytest.raises(ValueError, match="Unknown environment"):
         mbd_b200.envs.get_env("nope")
     with pytest.raises(NotImplementedError):
-        mbd_b200.envs.get_env("ant")
+        mbd_b200.envs.get_env("pushT")   # the one `generalized`-backend env
 
 
 def test_reset_is_the_reference_chain():
