@@ -8,8 +8,18 @@ softmax weighted mean + update.  value = Nsample*Hsample / t_step, whole job ove
   python bench.py [--gpus N --steps K --warmup W]        # under torchrun for N > 1
   python bench.py --impl reference ...                   # the CPU restatement (oracle) arm
 
-Timing: per-step CUDA events on the launching (current) stream, >= 3 warm-ups, L2 flushed
-(256 MiB memset, untimed) between steps, barrier + synchronize on both sides, max over ranks.
+Timing: CUDA events recorded on the launching stream by the C launch sequence itself (before the step, after the
+rollout kernel, after the step), >= 3 warm-ups, L2 flushed (256 MiB memset, untimed) between steps, barrier +
+synchronize on both sides, max over ranks.
+
+What the one JSON line carries beyond the contract:
+  value / e2e        weak scaling (8192 samples per GPU); `strong` = the same measurement with 8192 samples IN TOTAL
+                     (BASELINE config 4: "humanoidrun Nsample=8192 sample-sharded across 8 GPUs")
+  parity_ok          N > 1: rank 0 re-runs the first steps of the chain UNSHARDED and compares the iterates bit for bit
+  e2e_solve          wall clock of run_diffusion(Args(env_name="humanoidrun", not_render=True)) / 299 — what the reference's
+                     own timing script measures (/root/reference/mbd/scripts/run_mbd.py:20-39)
+  roofline           the mandated HBM figure; roofline_fp32 (against the FFMA peak MEASURED in this run) and
+                     roofline_issue are the ones that bind
 """
 from __future__ import annotations
 
@@ -29,7 +39,9 @@ sys.path.insert(0, ROOT)
 ENV_NAME, NSAMPLE, HSAMPLE, NDIFFUSE, TEMP = "humanoidrun", 8192, 50, 300, 0.1
 NU, NFRAMES = 17, 7
 BYTES_PER_ENV_STEP = 4 * NU + 4  # action row read once + reward written once = 72 B
+FLOP_PER_SUBSTEP = 9336          # algorithmic flops per sample and XPBD substep (tests/test_pk_host.py::test_algorithmic_operation_count)
 METRIC = "env-steps/sec (Nsample x Hsample per diffusion step) on humanoidrun"
+WORKLOAD = f"{ENV_NAME} Nsample={NSAMPLE} Hsample={HSAMPLE} n_frames={NFRAMES} Ndiffuse={NDIFFUSE}"
 
 
 def _peaks():
@@ -51,10 +63,6 @@ def _ncu_summary():
         except Exception:  # noqa: BLE001
             return {}
     return {}
-
-
-def _ncu_traffic():
-    return _ncu_summary().get("dram_bytes_per_launch")
 
 
 class ClockSampler:
@@ -91,40 +99,50 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def _oracle_setup():
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host threads
+# ---------------------------------------------------------------------------------------------------------------------
+def _host_threads() -> int:
+    """every hardware thread this process may run on — torchrun exports OMP_NUM_THREADS=1, which round 1 obeyed by accident"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def time_cpu_oracle(n_samples: int, steps: int, warmup: int):
+    """The CPU restatement of the same diffusion step (sampling + rollouts + statistics) on `n_samples` of the Nsample
+    rollouts per step.  Threads are set explicitly; `warmup` >= 3 untimed steps bring up the OpenMP team, the pages and the
+    clocks (round 1's readings moved 5x without them); the value is the MEDIAN step time.  Returns (env-steps/s, s, threads)."""
     import mbd_b200
     from mbd_b200 import prng
     from oracle import oracle as orc
     from oracle import planner as opl
+    native = orc.use_native()
     env = mbd_b200.envs.get_env(ENV_NAME)
     rng, rng_reset = prng.split(prng.PRNGKey(0))
-    st = env.reset(rng_reset).pipeline_state.raw
-    rng_exp, _ = prng.split(rng)
-    return env, st, rng_exp, orc, opl
-
-
-def time_cpu_oracle(n_samples: int, steps: int, warmup: int):
-    """The CPU restatement of the same diffusion step (sampling + rollouts + statistics) on all
-    host threads, on a bounded sample of n_samples of the Nsample rollouts per step."""
-    env, st, key, orc, opl = _oracle_setup()
-    from mbd_b200 import prng
+    q = env.sys.init_q.astype(np.float32)
+    r, r1, r2 = prng.split(rng_reset, 3)   # humanoidrun.reset on the host (no GPU needed for this arm)
+    st = env.pipeline_init(q + prng.uniform(r1, (env.sys.q_size(),), minval=-0.01, maxval=0.01),
+                           prng.uniform(r2, (env.sys.qd_size(),), minval=-0.01, maxval=0.01)).raw
+    key, _ = prng.split(rng)
     _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, NDIFFUSE)
     oenv = opl.OracleEnv("xpbd", NU, blob=env.blob, state=st)
-    threads = orc.num_threads()
+    threads = _host_threads()
     Yb = np.zeros(HSAMPLE * NU, np.float32)
     times = []
     i = NDIFFUSE - 1
-    for it in range(warmup + steps):
+    for it in range(max(warmup, 3) + steps):
         key, k = prng.split(key)
         t0 = time.perf_counter()
-        o = opl.reverse_once(oenv, k, n_samples, HSAMPLE, float(sigmas[i]), Yb, TEMP, alphas, alphas_bar, i)
+        o = opl.reverse_once(oenv, k, n_samples, HSAMPLE, float(sigmas[i]), Yb, TEMP, alphas, alphas_bar, i, nthreads=threads)
         dt = time.perf_counter() - t0
         Yb = o["Ybar_im1"]
         i -= 1
-        if it >= warmup:
+        if it >= max(warmup, 3):
             times.append(dt)
-    t = float(np.mean(times))
-    return n_samples * HSAMPLE / t, t, threads
+    t = float(np.median(times))
+    return n_samples * HSAMPLE / t, t, threads, ("-O2 -march=native" if native else "-O2 -mavx2 -mfma")
 
 
 def run_reference(args):
@@ -134,28 +152,34 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.cpu_samples
-    val, t, threads = time_cpu_oracle(n, args.steps, args.warmup)
+    val, t, threads, flags = time_cpu_oracle(n, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "warmup": max(args.warmup, 3), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{ENV_NAME} Nsample={NSAMPLE} Hsample={HSAMPLE} n_frames={NFRAMES} Ndiffuse={NDIFFUSE}",
-                   "note": "CPU restatement (JAX/Brax unavailable): C oracle, OpenMP over samples"},
+        "config": {"workload": WORKLOAD,
+                   "note": f"CPU restatement (JAX/Brax unavailable): C oracle ({flags}, scalar, one rollout per OpenMP iteration), "
+                           f"{threads} threads, median of {args.steps} steps; each step = a bounded sample of {n} of the {NSAMPLE} rollouts"},
         "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} of {NSAMPLE} rollouts x {HSAMPLE} env steps per step, {args.steps} steps"},
+                         "sample": f"{n} of {NSAMPLE} rollouts x {HSAMPLE} env steps per step, median of {args.steps} steps after "
+                                   f"{max(args.warmup, 3)} warm-ups"},
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
     import mbd_b200
-    from mbd_b200 import prng
+    from mbd_b200 import ops, prng
     from mbd_b200.planners import engine as eng
+    from mbd_b200.planners.mbd_planner import Args, run_diffusion
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -164,128 +188,177 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_total = NSAMPLE * world if args.scaling == "weak" else NSAMPLE
     env = mbd_b200.envs.get_env(ENV_NAME)
     rng, rng_reset = prng.split(prng.PRNGKey(0))
     state_init = env.reset(rng_reset)
     _, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, NDIFFUSE)
-    e = eng.DiffusionEngine(env, n_total, HSAMPLE, TEMP, False, state_init)
-    HNu = HSAMPLE * NU
     rng_exp, _ = prng.split(rng)
+    keys = eng.key_chain(rng_exp, NDIFFUSE)
+    HNu = HSAMPLE * NU
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = [ops.Event() for _ in range(3)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def chain(nsteps, timed, host_io):
-        """runs nsteps diffusion steps of the real chain starting at i = Ndiffuse-1; returns summed ms"""
-        key = rng_exp
-        Ybar = torch.zeros(HNu, device=dev)
-        out = torch.empty(HNu, device=dev)
+    def make_engine(n_total, single=False):
+        e = eng.DiffusionEngine(env, n_total, HSAMPLE, TEMP, False, state_init, Ndiffuse=NDIFFUSE, emulate=(1, 0, None) if single else None)
+        e.load_schedule(keys, sigmas, alphas, alphas_bar)
+        e.set_step(NDIFFUSE - 1)
+        return e
+
+    def chain(e, nsteps, timed, host_io):
+        """nsteps diffusion steps of the real seed-0 chain from wherever the device step counter stands; returns summed
+        (step ms, rollout-kernel ms)"""
         h_in = torch.zeros(HNu, dtype=torch.float32).pin_memory()
         h_out = torch.zeros(HNu + 1, dtype=torch.float32).pin_memory()
         tot, kern = 0.0, 0.0
-        i = NDIFFUSE - 1
+        i = int(e.ctl[0].item())
+        if host_io:
+            h_in.copy_(e.Ybars[i].cpu())
         for _ in range(nsteps):
-            key, k = prng.split(key)
-            coef = eng.update_coef(alphas, alphas_bar, i)
             flush.fill_(1)
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
-            if host_io:  # the reference-facing call with HOST buffers: H2D of the iterate, D2H of result + reward
-                Ybar.copy_(h_in, non_blocking=True)
-            if e.single_kernel:      # one cooperative kernel does the whole step
-                e.reverse_once(k, float(sigmas[i]), Ybar, coef, out=out)
-                e2.record()
+            if host_io:   # the reference-facing call with HOST buffers: H2D of the iterate, D2H of result + reward
+                ev[0].record()
+                e.Ybars[i].copy_(h_in, non_blocking=True)
+                ops.step_launch(e._plan_c)
+                h_out[:HNu].copy_(e.Ybars[i - 1], non_blocking=True)
+                h_out[HNu:].copy_(e.rew_hist[i:i + 1], non_blocking=True)
+                ev[2].record()
             else:
-                e.rollout_phase(k, float(sigmas[i]), Ybar)
-                e2.record()
-                e.gather_phase()
-                e.reduce_phase(Ybar, coef, out)
-            if host_io:
-                h_out[:HNu].copy_(out, non_blocking=True)
-                h_out[HNu:].copy_(e.scalars[:1], non_blocking=True)
-            e1.record()
-            e1.synchronize()
+                ops.step_launch_timed(e._plan_c, ev[0], ev[1], ev[2])
+            ev[2].synchronize()
             if host_io:
                 h_in.copy_(h_out[:HNu])
-            Ybar, out = out, Ybar
             if timed:
-                tot += e0.elapsed_time(e1)
-                kern += e0.elapsed_time(e2)
+                tot += ev[0].elapsed_ms(ev[2])
+                kern += ev[0].elapsed_ms(ev[1])
             i -= 1
         return tot, kern
 
-    chain(args.warmup, False, False)
-    barrier()
+    def measure(n_total):
+        """(ms per step, rollout-kernel ms, e2e ms per step, parity_ok or None, engine) for n_total samples over `world` ranks"""
+        e = make_engine(n_total)
+        chain(e, args.warmup, False, False)
+        barrier()
+        tot, kern = chain(e, args.steps, True, False)
+        barrier()
+        chain(e, 1, False, True)
+        barrier()
+        e2e, _ = chain(e, args.steps, True, True)
+        barrier()
+        e.check_exchange()
+        t = torch.tensor([tot, kern, e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot, kern, e2e = (float(v) / args.steps for v in t.tolist())
+        parity = None
+        if world > 1:
+            # rank 0 re-runs the first steps of the same chain UNSHARDED: the sharded iterates must be the same bits
+            ok = 1
+            ncheck = min(3, args.warmup + args.steps)
+            if rank == 0:
+                e1 = make_engine(n_total, single=True)
+                for _ in range(ncheck):
+                    e1.step()
+                torch.cuda.synchronize()
+                a = e.Ybars[NDIFFUSE - 1 - ncheck:NDIFFUSE - 1].cpu().numpy().view(np.uint32)
+                b = e1.Ybars[NDIFFUSE - 1 - ncheck:NDIFFUSE - 1].cpu().numpy().view(np.uint32)
+                ok = int(np.array_equal(a, b))
+                del e1
+            okt = torch.tensor([ok], device=dev)
+            dist.broadcast(okt, 0)
+            parity = bool(okt.item())
+        return tot, kern, e2e, parity, e
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    tot_ms, kern_ms = chain(args.steps, True, False)
-    barrier()
+    n_weak = NSAMPLE * world if args.scaling == "weak" else NSAMPLE
+    ms_step, kern_ms, e2e_ms, parity_ok, e = measure(n_weak)
     clocks = sampler.stop() if rank == 0 else None
-    chain(1, False, True)
-    barrier()
-    e2e_ms, _ = chain(args.steps, True, True)
-    barrier()
-    t = torch.tensor([tot_ms, kern_ms, e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tot_ms, kern_ms, e2e_ms = (float(v) for v in t.tolist())
+    n_local = e.n_local
+    del e
+    strong = None
+    if world > 1 and args.scaling == "weak":
+        s_ms, s_kern, s_e2e, s_par, es = measure(NSAMPLE)
+        strong = {"metric": METRIC, "value": NSAMPLE * HSAMPLE / (s_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": s_ms,
+                  "kernel_ms": s_kern, "e2e_value": NSAMPLE * HSAMPLE / (s_e2e * 1e-3), "global_samples": NSAMPLE,
+                  "samples_per_gpu": es.n_local, "parity_ok": s_par,
+                  "note": "BASELINE config 4: humanoidrun Nsample=8192 sample-sharded across the ranks (strong scaling)"}
+        del es
+    # ---- the whole solve through the reference-facing API (run_mbd.py:20-39 times exactly this call)
+    solve = None
+    if not args.no_solve:
+        barrier()
+        t0 = time.perf_counter()
+        rew_final = run_diffusion(Args(env_name=ENV_NAME, not_render=True), log_every=10 ** 9)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        w = torch.tensor([wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        wall = float(w.item())
+        solve = {"wall_s": wall, "ms_per_step": wall / (NDIFFUSE - 1) * 1e3, "value": NSAMPLE * HSAMPLE * (NDIFFUSE - 1) / wall,
+                 "unit": "env-steps/s", "rew_final": float(rew_final), "global_samples": NSAMPLE,
+                 "what": "time.time() around run_diffusion(Args(env_name='humanoidrun', not_render=True)): env + model construction, "
+                         "schedule upload, graph capture, 299 steps, final rollout"}
     if rank == 0:
-        ms_step = tot_ms / args.steps
-        value = n_total * HSAMPLE / (ms_step * 1e-3)
-        e2e_val = n_total * HSAMPLE / (e2e_ms / args.steps * 1e-3)
-        kern_s = kern_ms / args.steps * 1e-3
-        alg_bytes = e.n_local * HSAMPLE * BYTES_PER_ENV_STEP  # per launch of the rollout kernel (per rank)
+        value = n_weak * HSAMPLE / (ms_step * 1e-3)
+        kern_s = kern_ms * 1e-3
+        alg_bytes = n_local * HSAMPLE * BYTES_PER_ENV_STEP  # per launch of the rollout kernel (per rank)
         peak, peak_src = _peaks()
         achieved = alg_bytes / kern_s / 1e9
+        summ = _ncu_summary()
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{ENV_NAME} Nsample={n_total} Hsample={HSAMPLE} n_frames={NFRAMES} Ndiffuse={NDIFFUSE} "
-                                   f"(steps i={NDIFFUSE - 1}..{NDIFFUSE - args.steps} of the real chain, seed 0)",
-                       "global_samples": n_total, "samples_per_gpu": e.n_local, "parallelism": f"sample-shard x{world}", "exchange": e.exchange,
-                       "l2": "flushed between steps (256 MiB memset, untimed)",
-                       "substeps_per_s": value * NFRAMES},
+            "config": {"workload": WORKLOAD, "chain": f"steps i={NDIFFUSE - 1 - args.warmup}..{NDIFFUSE - args.warmup - args.steps} of the real seed-0 chain",
+                       "global_samples": n_weak, "samples_per_gpu": n_local, "parallelism": f"sample-shard x{world}",
+                       "exchange": "none" if world == 1 else "NVLink peer loads inside the tail kernels (symmetric memory)",
+                       "l2": "flushed between steps (256 MiB memset, untimed)", "substeps_per_s": value * NFRAMES},
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": HNu * 4 + 8, "d2h_bytes_per_step": HNu * 4 + 4},
-            "gpu_launches": e.launches_last_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": ("k_reverse_step_wpl (sampling + rollouts + statistics + weighted mean + update, one launch)"
-                                                   if e.single_kernel else f"{_ncu_summary().get('kernel', 'k_rollout_wpl<true,...>')} (fused sampling + rollouts)"), "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _ncu_traffic(), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_s * 1e3,
-                         "note": "path is fp32-issue bound, not HBM bound (SURVEY F7): see DESIGN.md roofline section"},
+            "e2e": {"value": n_weak * HSAMPLE / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": HNu * 4,
+                    "d2h_bytes_per_step": HNu * 4 + 4},
+            "gpu_launches": 3 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": f"{summ.get('kernel', 'k_rollout_wpl<true,...>')} (fused sampling + rollouts)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": summ.get("dram_bytes_per_launch"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
+                         "note": "path is fp32-issue bound, not HBM bound (SURVEY F7): see roofline_fp32 / roofline_issue and DESIGN.md"},
         }
-        # the roofline that actually binds (DESIGN.md section 4): warp-instruction issue slots.
-        # instructions per launch come from the committed ncu capture of the same kernel/workload.
-        wi = _ncu_summary().get("warp_instructions")
-        if wi and e.n_local == NSAMPLE:
-            clk = (clocks or {}).get("sm_mhz") or 1965.0
+        if parity_ok is not None:
+            line["parity_ok"] = parity_ok
+        if strong is not None:
+            line["strong"] = strong
+        if solve is not None:
+            line["e2e_solve"] = solve
+        wi = summ.get("warp_instructions")
+        clk = float((clocks or {}).get("sm_mhz") or 1965.0)
+        if wi and n_local == NSAMPLE:
             peak_issue = 148 * 4 * clk * 1e6  # 1 warp-instruction per SM sub-partition per cycle
             line["roofline_issue"] = {"bound": "fp32 issue slots", "achieved": wi / kern_s, "peak": peak_issue, "unit": "warp-inst/s",
                                       "frac": wi / kern_s / peak_issue, "warp_instructions_per_launch": wi,
                                       "source": "profiles/rollout_kernel_summary.json (ncu smsp__inst_executed.sum)"}
-        # fp32 roofline from the ALGORITHMIC flop count (9336 per sample and XPBD substep on humanoidrun, counted by running
-        # the physics with an operation-counting scalar type: tests/test_pk_host.py::test_algorithmic_operation_count)
         try:
-            clk_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
-            flop = float(e.n_local) * HSAMPLE * NFRAMES * 9336.0
-            peak_tf = 148 * 128 * 2 * clk_mhz * 1e6 / 1e12   # 128 fp32 lanes per SM, FMA = 2 flop
-            line["roofline_fp32"] = {"bound": "fp32 pipe", "achieved": flop / kern_s / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                                     "frac": flop / kern_s / 1e12 / peak_tf, "flop_per_sample_substep": 9336,
+            measured_tf = ops.ffma_peak(dev)
+            flop = float(n_local) * HSAMPLE * NFRAMES * FLOP_PER_SUBSTEP
+            nominal_tf = 148 * 128 * 2 * clk * 1e6 / 1e12
+            line["roofline_fp32"] = {"bound": "fp32 pipe", "achieved": flop / kern_s / 1e12, "peak": measured_tf, "unit": "TFLOP/s",
+                                     "frac": flop / kern_s / 1e12 / measured_tf, "peak_source": "measured in this run (mbd_ffma_peak: 16 "
+                                     "independent FFMA chains per thread, 2048 threads per SM)", "nominal_peak": nominal_tf,
+                                     "flop_per_sample_substep": FLOP_PER_SUBSTEP,
                                      "note": "algorithmic flops (mul, add 1; fma 2; div, rcp, sqrt 1); the device executes ~15 % more"}
-        except Exception:  # noqa: BLE001 - never lose the bench line over an explanatory field
-            pass
+        except Exception as ex:  # noqa: BLE001 - never lose the bench line over an explanatory field
+            line["roofline_fp32"] = {"error": str(ex)}
         if world == 1 and not args.no_cpu_baseline:
-            val, tcpu, threads = time_cpu_oracle(args.cpu_samples, 3, 1)
+            val, tcpu, threads, flags = time_cpu_oracle(args.cpu_samples, 5, 3)
             line["cpu_baseline"] = {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{args.cpu_samples} of {NSAMPLE} rollouts x {HSAMPLE} env steps per step, 3 steps "
-                                              f"(CPU restatement; JAX/Brax unavailable)"}
+                                    "sample": f"{args.cpu_samples} of {NSAMPLE} rollouts x {HSAMPLE} env steps per step, median of 5 steps "
+                                              f"after 3 warm-ups (CPU restatement, {flags}; JAX/Brax unavailable)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -300,10 +373,11 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-samples", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-solve", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.steps + args.warmup >= NDIFFUSE:
-        raise SystemExit("steps + warmup must be < Ndiffuse")
+    args.warmup = max(args.warmup, 3)
+    if 2 * args.steps + args.warmup + 2 >= NDIFFUSE:
+        raise SystemExit("2*steps + warmup + 2 must be < Ndiffuse")
     if args.impl == "reference":
         run_reference(args)
     else:

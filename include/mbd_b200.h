@@ -28,6 +28,8 @@ typedef void* mbd_stream; /* cudaStream_t */
 
 /* ABI/layout self-description (cross-checked against the Python packer in tests/test_abi.py) */
 int mbd_layout_info(int32_t* out, int n);
+/* sizeof / offsetof of the structs passed by pointer (mbd_step_params, mbd_step_ctl, mbd_step_plan), same cross-check */
+int mbd_abi_sizes(int32_t* out, int n);
 const char* mbd_last_error(void);
 int mbd_device_count(void);
 /* rollout kernel mapping: 0 = auto (by shard size), 1 = v1 (one link per lane), 2/3/4 = v2 (one link per
@@ -132,6 +134,65 @@ int mbd_test_arith(int op, const float* a_dev, const float* b_dev, float* out_de
  * mbd_planner.py:100,130-133.  coef = {sqrt(ab_i), 1/(1-ab_i), 1-ab_i, 1/sqrt(alpha_i), sqrt(ab_{i-1})}. */
 int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5],
                float* Ybar_im1_dev, mbd_stream s);
+
+/* ---- one diffusion step as THREE parameterless launches (CUDA-graph capturable) -------------------------------------
+ * reverse_once (mbd_planner.py:97-135) for any rank count: (1) sampling + rollouts, (2) global reward statistics /
+ * demo blend / softmax in one 8-CTA thread-block cluster that pulls the peers' per-sample returns over NVLink itself,
+ * (3) weighted-mean runs whose last CTA folds the tree, exchanges the rank partials over NVLink and applies the update
+ * lines 130-133.  Everything that changes from step to step lives in DEVICE memory: params_dev[i] = {Y0s_rng key
+ * (mbd_planner.py:103), sigmas[i], the five schedule scalars of mbd_update}, ctl_dev->i = the step index (the host loop
+ * variable of mbd_planner.py:141), decremented by the last thread of launch (3); the iterate Ybar_i is row i of Ybars_dev
+ * and the result is written to row i - 1, rews.mean() to rew_hist_dev[i].  The host therefore launches the same three
+ * kernels Ndiffuse-1 times (or replays one captured graph) without touching a parameter. */
+typedef struct mbd_step_params { uint32_t key[2]; float sigma; float coef[5]; } mbd_step_params; /* 32 bytes */
+#define MBD_STEP_MAX_COLBLOCKS 27 /* H*Nu <= 27*256 */
+typedef struct mbd_step_ctl {      /* 128 bytes, zero-initialised by the caller except `i` */
+  int32_t i;                       /* current step index (Ndiffuse-1 ... 1) */
+  uint32_t epoch;                  /* cross-GPU rendezvous counter (advanced once per step) */
+  uint32_t err;                    /* set to 1 when a cross-GPU rendezvous timed out (outputs are NaN-poisoned) */
+  uint32_t pad;
+  uint32_t ticket[28];             /* "last CTA done" tickets: per column block, [27] over the column blocks... see step_tail.cuh */
+} mbd_step_ctl;
+typedef struct mbd_step_plan {
+  const mbd_model* model;            /* Brax-positional env; NULL = car2d (car_params_dev, state_init_dev = x0[3]) */
+  const float* car_params_dev;
+  const float* state_init_dev;       /* [L,13] */
+  const mbd_step_params* params_dev; /* [Ndiffuse] */
+  mbd_step_ctl* ctl_dev;
+  float* Ybars_dev;                  /* [Ndiffuse, H*Nu] */
+  float* rew_hist_dev;               /* [Ndiffuse] or NULL */
+  int32_t n_total, n_begin, n_local, H, nu;
+  float temp, rew_xref;
+  const float* xref_dev;             /* demo reference (enable_demo) or NULL */
+  int32_t href;
+  float* Y0s_dev;                    /* [n_local, H*Nu] */
+  float* rews_dev;                   /* [n_local]; P > 1: inside this rank's symmetric buffer at off_rews_words */
+  float* logpd_dev;                  /* [n_local] or NULL; P > 1: at off_logpd_words */
+  float* rews_all_dev;               /* [n_total] (unused when P == 1) */
+  float* logpd_all_dev;              /* [n_total] or NULL */
+  float* logp_dev;                   /* [n_total] scratch */
+  float* weights_dev;                /* [n_local] */
+  float* runs_dev;                   /* [ceil(n_local/64), H*Nu] */
+  float* partial_dev;                /* [H*Nu]; P > 1: inside the symmetric buffer at off_partial_words */
+  float* scalars_dev;                /* [4] = {rews.mean(), rew_std, max logit, sum exp} of the last step */
+  int32_t P, rank;
+  const uint64_t* peer_base_ptrs;    /* host array [P]: base address of every rank's symmetric buffer (NULL when P == 1) */
+  uint64_t off_rews_words, off_logpd_words, off_partial_words, off_flags_words;  /* flags: 2 rows of 8 words, zeroed */
+  uint64_t timeout_cycles;           /* cross-GPU rendezvous timeout in SM cycles; 0 = default (~20 s) */
+} mbd_step_plan;
+int mbd_step_launch(const mbd_step_plan* plan, mbd_stream s);
+/* the same three launches with CUDA events (mbd_event_create) recorded before (1), between (1) and (2), after (3): lets a
+ * caller time the rollout kernel inside the real step on the launching stream (bench.py's roofline) */
+int mbd_step_launch_ev(const mbd_step_plan* plan, void* ev_before, void* ev_mid, void* ev_after, mbd_stream s);
+void* mbd_event_create(void);
+void mbd_event_destroy(void* ev);
+int mbd_event_record(void* ev, mbd_stream s);
+int mbd_event_sync(void* ev);
+float mbd_event_elapsed_ms(void* ev_a, void* ev_b);
+
+/* Measured fp32 FFMA throughput of the current device in TFLOP/s (16 independent chains per thread, 2048 threads per SM):
+ * the denominator of bench.py's fp32 roofline.  Synchronises the stream. */
+int mbd_ffma_peak(float* scratch_dev, int iters, float* tflops_out, mbd_stream s);
 
 #ifdef __cplusplus
 }

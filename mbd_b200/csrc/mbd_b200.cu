@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stddef.h>
 #include <string.h>
 
 #include <type_traits>
@@ -23,6 +24,7 @@
 #include "xpbd_device.cuh"
 #include "xpbd_wpl.cuh"
 #include "xpbd_pk.cuh"
+#include "step_tail.cuh"
 
 namespace mbd {
 
@@ -68,6 +70,8 @@ __device__ __forceinline__ float sample_elem(uint32_t k0, uint32_t k1, uint32_t 
   return clampf(y, -1.0f, 1.0f);
 }
 
+struct SampleParams { uint32_t k0, k1; float sigma; const float* Ybar; };
+
 __global__ void k_sample(uint32_t k0, uint32_t k1, uint32_t total, uint32_t begin, uint32_t count, int HNu, float sigma,
                          const float* __restrict__ Ybar, float* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +99,11 @@ struct RolloutArgs {
   int n_total, n_begin;
   float sigma;
   const float* Ybar;       // [H*nu]
+  // fused sampling with DEVICE-resident step parameters (graph-capturable step, step_tail.cuh): when sp != null the key,
+  // sigma and the iterate row are taken from sp[ctl->i] / Ybars + ctl->i * HNu instead of the by-value fields above
+  const mbd_step_params* sp;
+  const mbd_step_ctl* ctl;
+  const float* Ybars;
   // v2 mapping: link owned by (warp, half) and the half-warp offset (in units of 4 lanes) of every link's row
   signed char wl[MBD_MAXL][2];
   unsigned long long offs;
@@ -103,6 +112,17 @@ struct RolloutArgs {
   int count_x;             // group barriers: 32 * (links that are not leaves with contacts), see SyncGroup
   int stagger;             // two-group CTA: cycles group 1 waits before its first step (experiment: de-phase the groups)
 };
+
+__device__ __forceinline__ SampleParams sample_params(const RolloutArgs& a, int HNu) {
+  SampleParams q;
+  q.k0 = a.k0; q.k1 = a.k1; q.sigma = a.sigma; q.Ybar = a.Ybar;
+  if (a.sp != nullptr) {
+    const int i = a.ctl->i;
+    q.k0 = a.sp[i].key[0]; q.k1 = a.sp[i].key[1]; q.sigma = a.sp[i].sigma;
+    q.Ybar = a.Ybars + (size_t)i * HNu;
+  }
+  return q;
+}
 
 template <bool FUSED, int CMAX>
 __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
@@ -123,12 +143,13 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
   if (FUSED) {
     // each CTA draws the noise of exactly its own samples, then reads it back after the barrier
     const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+    const SampleParams sq = sample_params(a, HNu);
     const int first = blockIdx.x * kSPB;
     const int cnt = min(kSPB, a.n - first) * HNu;
     for (int e = tid; e < cnt; e += kRolloutThreads) {
       int ns = first + e / HNu, j = e % HNu;
       uint32_t idx = (uint32_t)(a.n_begin + ns) * (uint32_t)HNu + (uint32_t)j;
-      a.Y0s[(size_t)ns * HNu + j] = sample_elem(a.k0, a.k1, idx, total, a.sigma, a.Ybar[j]);
+      a.Y0s[(size_t)ns * HNu + j] = sample_elem(sq.k0, sq.k1, idx, total, sq.sigma, sq.Ybar[j]);
     }
     __syncthreads();
   }
@@ -267,12 +288,13 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
 
   if (FUSED) {
     const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+    const SampleParams sq = sample_params(a, HNu);
     const int first = blockIdx.x * kLpl * GROUPS;
     const int cnt = min(kLpl * GROUPS, a.n - first) * HNu;
     for (int e = tid; e < cnt; e += nthreads) {
       int ns = first + e / HNu, j = e % HNu;
       uint32_t idx = (uint32_t)(a.n_begin + ns) * (uint32_t)HNu + (uint32_t)j;
-      a.Y0s[(size_t)ns * HNu + j] = sample_elem(a.k0, a.k1, idx, total, a.sigma, a.Ybar[j]);
+      a.Y0s[(size_t)ns * HNu + j] = sample_elem(sq.k0, sq.k1, idx, total, sq.sigma, sq.Ybar[j]);
     }
     __syncthreads();
   }
@@ -473,12 +495,13 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
 
   if (FUSED) {
     const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+    const SampleParams sq = sample_params(a, HNu);
     const int first = blockIdx.x * kPkSamples;
     const int cnt = min(kPkSamples, a.n - first) * HNu;
     for (int e = tid; e < cnt; e += nthreads) {
       int ns = first + e / HNu, j = e % HNu;
       uint32_t idx = (uint32_t)(a.n_begin + ns) * (uint32_t)HNu + (uint32_t)j;
-      a.Y0s[(size_t)ns * HNu + j] = sample_elem(a.k0, a.k1, idx, total, a.sigma, a.Ybar[j]);
+      a.Y0s[(size_t)ns * HNu + j] = sample_elem(sq.k0, sq.k1, idx, total, sq.sigma, sq.Ybar[j]);
     }
   }
   __syncthreads();   // the duplicated table and (FUSED) this CTA's action rows are complete
@@ -626,6 +649,7 @@ struct CarArgs {
   const float* params; const float* x0; float* Y0s; int n, H;
   float* rewss; float* rews; const float* xref; int href; float* logpd; float* traj;
   int fused; uint32_t k0, k1; int n_total, n_begin; float sigma; const float* Ybar;
+  const mbd_step_params* sp; const mbd_step_ctl* ctl; const float* Ybars;   // device-resident step parameters (see RolloutArgs)
 };
 __global__ void k_car2d(CarArgs a) {
   __shared__ float sp[2 * kCarObs + 4];
@@ -636,6 +660,11 @@ __global__ void k_car2d(CarArgs a) {
   const float orad = sp[2 * kCarObs], dt = sp[2 * kCarObs + 1], hdt = sp[2 * kCarObs + 2], sdt = sp[2 * kCarObs + 3];
   const int HNu = a.H * 2;
   const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+  uint32_t ck0 = a.k0, ck1 = a.k1; float csigma = a.sigma; const float* cYbar = a.Ybar;
+  if (a.sp != nullptr) {
+    const int si = a.ctl->i;
+    ck0 = a.sp[si].key[0]; ck1 = a.sp[si].key[1]; csigma = a.sp[si].sigma; cYbar = a.Ybars + (size_t)si * HNu;
+  }
   float q[3] = {a.x0[0], a.x0[1], a.x0[2]};
   float sum = 0.0f, acc = 0.0f;
   for (int t = 0; t < a.H; ++t) {
@@ -643,8 +672,8 @@ __global__ void k_car2d(CarArgs a) {
     float u0, u1;
     if (a.fused) {
       uint32_t idx = (uint32_t)(a.n_begin + i) * (uint32_t)HNu + (uint32_t)(2 * t);
-      u0 = sample_elem(a.k0, a.k1, idx, total, a.sigma, a.Ybar[2 * t]);
-      u1 = sample_elem(a.k0, a.k1, idx + 1, total, a.sigma, a.Ybar[2 * t + 1]);
+      u0 = sample_elem(ck0, ck1, idx, total, csigma, cYbar[2 * t]);
+      u1 = sample_elem(ck0, ck1, idx + 1, total, csigma, cYbar[2 * t + 1]);
       ur[0] = u0; ur[1] = u1;
     } else {
       u0 = ur[0]; u1 = ur[1];
@@ -1137,6 +1166,18 @@ int mbd_layout_info(int32_t* out, int n) {
   return cnt;
 }
 
+// sizeof / offsetof of the structs that cross the ABI by pointer (cross-checked against the ctypes mirrors in tests/test_abi.py)
+int mbd_abi_sizes(int32_t* out, int n) {
+  const int32_t v[] = {(int32_t)sizeof(mbd_step_params), (int32_t)sizeof(mbd_step_ctl), (int32_t)sizeof(mbd_step_plan),
+                       (int32_t)offsetof(mbd_step_plan, n_total), (int32_t)offsetof(mbd_step_plan, xref_dev),
+                       (int32_t)offsetof(mbd_step_plan, Y0s_dev), (int32_t)offsetof(mbd_step_plan, P),
+                       (int32_t)offsetof(mbd_step_plan, peer_base_ptrs), (int32_t)offsetof(mbd_step_plan, timeout_cycles),
+                       (int32_t)offsetof(mbd_step_ctl, ticket)};
+  const int cnt = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < cnt && i < n; ++i) out[i] = v[i];
+  return cnt;
+}
+
 mbd_model* mbd_model_create(const uint32_t* blob_host, size_t nwords) {
   if (!blob_host || nwords != MBD_BLOB_WORDS || blob_host[MBD_H_MAGIC] != MBD_MODEL_MAGIC) {
     snprintf(g_err, sizeof(g_err), "mbd_model_create: bad blob (words=%zu)", nwords);
@@ -1414,6 +1455,124 @@ int mbd_peer_gather(const uint64_t* peer_base_ptrs, int P, int rank, size_t src_
   if (grid > 64) grid = 64;
   mbd::k_peer_gather<<<grid, 256, 0, (cudaStream_t)s>>>(a);
   CK(cudaGetLastError());
+  return MBD_OK;
+}
+
+// launches (2) and (3) of a step: statistics / softmax (one cluster) and weighted mean + update ("last CTA done")
+static int step_tail_launch(const mbd_step_plan* pl, cudaStream_t st) {
+  const int HNu = pl->H * pl->nu;
+  const bool demo = pl->xref_dev != nullptr;
+  mbd::TailArgs t;
+  memset(&t, 0, sizeof(t));
+  t.sp = pl->params_dev; t.ctl = pl->ctl_dev; t.Ybars = pl->Ybars_dev; t.rew_hist = pl->rew_hist_dev;
+  t.N = pl->n_total; t.n_begin = pl->n_begin; t.n_local = pl->n_local; t.HNu = HNu;
+  t.temp = pl->temp; t.rew_xref = pl->rew_xref; t.demo = demo ? 1 : 0;
+  t.Y0s = pl->Y0s_dev; t.rews = pl->rews_dev; t.logpd = pl->logpd_dev;
+  t.rews_all = pl->P == 1 ? pl->rews_dev : pl->rews_all_dev;
+  t.logpd_all = pl->P == 1 ? pl->logpd_dev : pl->logpd_all_dev;
+  t.logp = pl->logp_dev; t.weights = pl->weights_dev; t.runs = pl->runs_dev; t.partial = pl->partial_dev; t.scalars = pl->scalars_dev;
+  t.P = pl->P; t.rank = pl->rank;
+  for (int r = 0; r < pl->P && pl->peer_base_ptrs; ++r) t.peer[r] = reinterpret_cast<float*>(pl->peer_base_ptrs[r]);
+  t.off_rews = pl->off_rews_words; t.off_logpd = pl->off_logpd_words; t.off_partial = pl->off_partial_words; t.off_flags = pl->off_flags_words;
+  t.timeout_cycles = pl->timeout_cycles ? pl->timeout_cycles : 40000000000ull;   // ~20 s: a dead peer, not a slow one
+  mbd::k_step_weights<<<mbd::kClusterCtas, mbd::kWeightsThreads, 0, st>>>(t);
+  CK(cudaGetLastError());
+  const int nruns = (pl->n_local + mbd::kTailRun - 1) / mbd::kTailRun;
+  dim3 grid(nruns, (HNu + mbd::kUpdThreads - 1) / mbd::kUpdThreads);
+  mbd::k_step_update<<<grid, mbd::kUpdThreads, 0, st>>>(t);
+  CK(cudaGetLastError());
+  return MBD_OK;
+}
+
+// ---- one diffusion step with device-resident parameters: three launches, CUDA-graph capturable --------------------------
+static int step_launch_impl(const mbd_step_plan* pl, cudaStream_t st, cudaEvent_t ev_mid) {
+  if (!pl || !pl->state_init_dev || !pl->params_dev || !pl->ctl_dev || !pl->Ybars_dev || !pl->Y0s_dev || !pl->rews_dev ||
+      !pl->rews_all_dev || !pl->logp_dev || !pl->weights_dev || !pl->runs_dev || !pl->partial_dev || !pl->scalars_dev)
+    return MBD_EINVAL;
+  if (pl->n_local <= 0 || pl->H <= 0 || pl->nu <= 0 || pl->n_begin < 0 || pl->n_begin + pl->n_local > pl->n_total) return MBD_EINVAL;
+  if (pl->P < 1 || pl->P > 8 || pl->rank < 0 || pl->rank >= pl->P || (pl->P > 1 && !pl->peer_base_ptrs)) return MBD_EINVAL;
+  const int HNu = pl->H * pl->nu;
+  if ((HNu + mbd::kUpdThreads - 1) / mbd::kUpdThreads > MBD_STEP_MAX_COLBLOCKS) return MBD_EINVAL;
+  if ((uint64_t)pl->n_total * (uint64_t)HNu >= 0xffffffffull) return MBD_EINVAL;
+  const bool demo = pl->xref_dev != nullptr;
+  if (demo && (pl->href <= 0 || !pl->logpd_dev || !pl->logpd_all_dev)) return MBD_EINVAL;
+  // 1. sampling + rollouts
+  if (pl->model) {
+    if (pl->model->nu != pl->nu) return MBD_EINVAL;
+    mbd::RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.blob = pl->model->blob_dev; a.state_init = pl->state_init_dev; a.Y0s = pl->Y0s_dev; a.n = pl->n_local; a.H = pl->H;
+    a.rews = pl->rews_dev; a.xref = pl->xref_dev; a.href = pl->href; a.logpd = demo ? pl->logpd_dev : nullptr;
+    a.n_total = pl->n_total; a.n_begin = pl->n_begin;
+    a.sp = pl->params_dev; a.ctl = pl->ctl_dev; a.Ybars = pl->Ybars_dev;
+    int rc = launch_rollout(true, a, pl->model, st);
+    if (rc != MBD_OK) return rc;
+  } else {
+    if (!pl->car_params_dev || pl->nu != 2) return MBD_EINVAL;
+    mbd::CarArgs a;
+    memset(&a, 0, sizeof(a));
+    a.params = pl->car_params_dev; a.x0 = pl->state_init_dev; a.Y0s = pl->Y0s_dev; a.n = pl->n_local; a.H = pl->H;
+    a.rews = pl->rews_dev; a.xref = pl->xref_dev; a.href = pl->href; a.logpd = demo ? pl->logpd_dev : nullptr;
+    a.fused = 1; a.n_total = pl->n_total; a.n_begin = pl->n_begin;
+    a.sp = pl->params_dev; a.ctl = pl->ctl_dev; a.Ybars = pl->Ybars_dev;
+    mbd::k_car2d<<<(pl->n_local + 63) / 64, 64, 0, st>>>(a);
+    CK(cudaGetLastError());
+  }
+  if (ev_mid) CK(cudaEventRecord(ev_mid, st));
+  return step_tail_launch(pl, st);
+}
+int mbd_step_launch(const mbd_step_plan* pl, mbd_stream s) { return step_launch_impl(pl, (cudaStream_t)s, nullptr); }
+
+// mbd_step_launch with CUDA events recorded before launch (1), between launch (1) and launch (2), and after launch (3):
+// bench.py times the rollout kernel inside the real step with them (torch.cuda.Event exposes no handle that a C launch
+// sequence could record into; the events come from mbd_event_create)
+int mbd_step_launch_ev(const mbd_step_plan* pl, void* ev_before, void* ev_mid, void* ev_after, mbd_stream s) {
+  cudaStream_t st = (cudaStream_t)s;
+  if (ev_before) CK(cudaEventRecord((cudaEvent_t)ev_before, st));
+  int rc = step_launch_impl(pl, st, (cudaEvent_t)ev_mid);
+  if (rc != MBD_OK) return rc;
+  if (ev_after) CK(cudaEventRecord((cudaEvent_t)ev_after, st));
+  return MBD_OK;
+}
+void* mbd_event_create(void) {
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  return (void*)e;
+}
+void mbd_event_destroy(void* e) { if (e) cudaEventDestroy((cudaEvent_t)e); }
+int mbd_event_record(void* e, mbd_stream s) { CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s)); return MBD_OK; }
+int mbd_event_sync(void* e) { CK(cudaEventSynchronize((cudaEvent_t)e)); return MBD_OK; }
+float mbd_event_elapsed_ms(void* a, void* b) {
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+// measured fp32 FFMA throughput of the current device in TFLOP/s (FMA = 2 flop); synchronises the stream
+int mbd_ffma_peak(float* scratch_dev, int iters, float* tflops_out, mbd_stream s) {
+  if (!scratch_dev || !tflops_out || iters <= 0) return MBD_EINVAL;
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = (cudaStream_t)s;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int grid = 2 * sms;
+  mbd::k_ffma_peak<<<grid, 1024, 0, st>>>(scratch_dev, iters / 8 + 1, 1.0000001f, 1e-9f);   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0, st));
+    mbd::k_ffma_peak<<<grid, 1024, 0, st>>>(scratch_dev, iters, 1.0000001f, 1e-9f);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  const double flop = 2.0 * 64.0 * (double)iters * 1024.0 * (double)grid;
+  *tflops_out = (float)(flop / (best * 1e-3) / 1e12);
   return MBD_OK;
 }
 

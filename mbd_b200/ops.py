@@ -186,3 +186,50 @@ def peer_gather(peer_ptrs, P, rank, src_off_words, count, flag_off_words, epoch,
 def update(partials, P, HNu, Ybar_i, coef, out):
     c = (ctypes.c_float * 5)(*[float(v) for v in coef])
     check(_lib.lib().mbd_update(_p(_dev(partials)), P, HNu, _p(_dev(Ybar_i)), c, _p(_dev(out)), _stream()), "mbd_update")
+
+
+def step_launch(plan: "_lib.StepPlan"):
+    """one diffusion step (three launches, parameters in device memory): mbd_step_launch"""
+    check(_lib.lib().mbd_step_launch(ctypes.byref(plan), _stream()), "mbd_step_launch")
+
+
+def ffma_peak(device: Optional[torch.device] = None, iters: int = 4096) -> float:
+    """measured fp32 FFMA throughput of the device in TFLOP/s (the fp32 roofline denominator)"""
+    _lib.require_gpu()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        scratch = torch.empty(1 << 20, device=dev)
+        out = ctypes.c_float(0.0)
+        check(_lib.lib().mbd_ffma_peak(_p(scratch), int(iters), ctypes.byref(out), _stream()), "mbd_ffma_peak")
+    return float(out.value)
+
+
+class Event:
+    """raw CUDA event owned by the library (mbd_event_*): recordable from inside the C launch sequence"""
+
+    def __init__(self):
+        self.h = _lib.lib().mbd_event_create()
+        if not self.h:
+            raise MbdError("mbd_event_create failed")
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                _lib.lib().mbd_event_destroy(ctypes.c_void_p(h))
+            except Exception:  # noqa: BLE001
+                pass
+
+    def record(self):
+        check(_lib.lib().mbd_event_record(ctypes.c_void_p(self.h), _stream()), "mbd_event_record")
+
+    def synchronize(self):
+        check(_lib.lib().mbd_event_sync(ctypes.c_void_p(self.h)), "mbd_event_sync")
+
+    def elapsed_ms(self, later: "Event") -> float:
+        return float(_lib.lib().mbd_event_elapsed_ms(ctypes.c_void_p(self.h), ctypes.c_void_p(later.h)))
+
+
+def step_launch_timed(plan: "_lib.StepPlan", before: Event, mid: Event, after: Event):
+    check(_lib.lib().mbd_step_launch_ev(ctypes.byref(plan), ctypes.c_void_p(before.h), ctypes.c_void_p(mid.h), ctypes.c_void_p(after.h),
+                                         _stream()), "mbd_step_launch_ev")

@@ -16,7 +16,7 @@ import torch.distributed as dist
 
 import mbd_b200
 from mbd_b200 import ops, prng
-from mbd_b200.planners.engine import DiffusionEngine, make_schedule, update_coef
+from mbd_b200.planners.engine import DiffusionEngine, key_chain, make_schedule
 
 try:  # tqdm is cosmetic
     from tqdm import tqdm
@@ -84,27 +84,28 @@ def run_diffusion(args: Args, log_every: int = 10, return_trajectory: bool = Fal
     if _is_main():
         print(f"init sigma = {sigmas[-1]:.2e}")
 
-    engine = DiffusionEngine(env, args.Nsample, args.Hsample, args.temp_sample, args.enable_demo, state_init)
-    dev = engine.device
+    engine = DiffusionEngine(env, args.Nsample, args.Hsample, args.temp_sample, args.enable_demo, state_init, Ndiffuse=args.Ndiffuse)
     HNu = args.Hsample * Nu
-    # all Ndiffuse-1 iterates live on the device; nothing is copied to the host inside the loop
-    Ybars = torch.zeros((args.Ndiffuse, HNu), device=dev)  # row N-1 = YN = 0; row i-1 receives Ybar_{i-1}
-    rews = torch.zeros(args.Ndiffuse, device=dev)
-
+    # Everything the loop of mbd_planner.py:138-148 feeds into reverse_once is uploaded ONCE: the Y0s_rng chain
+    # (rng, Y0s_rng = split(rng) per step, :103), sigmas[i] and the schedule scalars.  engine.Ybars row N-1 = YN = 0 and
+    # row i-1 receives Ybar_{i-1}; one step is captured in a CUDA graph and replayed, nothing is copied to the host inside
+    # the loop.
     rng_exp, rng = prng.split(rng)
-    rng_loop = rng_exp
+    engine.load_schedule(key_chain(rng_exp, args.Ndiffuse), sigmas, alphas, alphas_bar)
+    engine.set_step(args.Ndiffuse - 1)
+    if os.environ.get("MBD_GRAPH", "1") != "0":
+        engine.capture()
     steps = range(args.Ndiffuse - 1, 0, -1)
     pbar = tqdm(steps, desc="Diffusing") if (tqdm is not None and _is_main()) else None
     for n_done, i in enumerate(pbar if pbar is not None else steps):
-        rng_loop, Y0s_rng = prng.split(rng_loop)  # mbd_planner.py:103
-        coef = update_coef(alphas, alphas_bar, i)
-        _, rew = engine.reverse_once(Y0s_rng, float(sigmas[i]), Ybars[i], coef, out=Ybars[i - 1])
-        rews[i].copy_(rew, non_blocking=True)
+        engine.step()
         if pbar is not None and (n_done % log_every == log_every - 1 or i == 1):
             # the reference formats rew every step (a device->host sync each step, mbd_planner.py:147);
             # here the sync is paid every `log_every` steps only
-            pbar.set_postfix({"rew": f"{rews[i].item():.2e}"})
+            pbar.set_postfix({"rew": f"{engine.rew_hist[i].item():.2e}"})
+            engine.check_exchange()
     engine.check_exchange()
+    Ybars = engine.Ybars
     Yi = Ybars[: args.Ndiffuse - 1].flip(0).reshape(args.Ndiffuse - 1, args.Hsample, Nu)  # jnp.array(Ybars) order
 
     if not args.not_render and _is_main():

@@ -77,7 +77,7 @@ class PathIntegralEngine(DiffusionEngine):
     def update_once(self, key, mu_0t: torch.Tensor, sigma: float, out: torch.Tensor):
         """returns (mu_0tm1 [device], sigma [host float], rews.mean() [device scalar])"""
         self.rollout_phase(key, sigma, mu_0t)                       # eps*sigma + mu_0t, clip, eval_us
-        ops.softmax_weights(self.rews_all, None, 0, self.n_local, self.temp, 0.0, self.weights, self.scalars, self.logp_scratch)
+        ops.softmax_weights(self.rews_local, None, 0, self.n_local, self.temp, 0.0, self.weights, self.scalars, self.logp_scratch)
         if self.update_method == "cem":
             order = torch.sort(self.weights, stable=True).indices   # jnp.argsort (stable, ascending)
             idx = order.flip(0)[:10]                                # [::-1][:10]

@@ -36,6 +36,25 @@ def build(force: bool = False) -> str:
     return so
 
 
+def use_native() -> bool:
+    """Switches this process to oracle/libmbd_oracle_native.so: the same source built `-O3 -march=native` ON THIS HOST
+    (bench.py's timed CPU arm; -ffp-contract=off is kept, so the results are the same bits).  Returns False — and keeps
+    the portable build — when the compile fails."""
+    global _LIB
+    import fcntl
+    so = os.path.join(_HERE, "libmbd_oracle_native.so")
+    try:
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            subprocess.run(["make", "-C", _HERE, "-B", "native"], check=True, capture_output=True)
+        L = ctypes.CDLL(so)
+        L.orc_num_threads.restype = ctypes.c_int
+        _LIB = L
+        return True
+    except Exception:  # noqa: BLE001
+        return False
+
+
 def lib():
     global _LIB
     if _LIB is None:

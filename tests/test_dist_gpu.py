@@ -1,5 +1,5 @@
 """Real multi-GPU check (needs >= 2 GPUs; skipped otherwise): a 2-rank NCCL run of the sharded
-engine gives bit-identical Ybar_im1 to the single-GPU run."""
+engine (exchange inside the tail kernels over NVLink peer memory) gives bit-identical iterates to the single-GPU run."""
 import os
 import socket
 import subprocess
@@ -26,20 +26,21 @@ demo = os.environ.get("MBD_TEST_DEMO", "0") == "1"   # BASELINE config 5: humano
 env = mbd_b200.envs.get_env("humanoidtrack" if demo else "humanoidrun")
 rng, rr = prng.split(prng.PRNGKey(0))
 st = env.reset(rr)
-_, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, 100)
-e = eng.DiffusionEngine(env, 2048, 50, 0.1, demo, st)
-Yb = torch.zeros(850, device="cuda")
-key = np.uint32([3, 1])
-outs = []
-for i in (99, 98, 97):
-    key2 = prng.split(key)[1]; key = prng.split(key)[0]
-    out, rew = e.reverse_once(key2, float(sigmas[i]), Yb, eng.update_coef(alphas, alphas_bar, i))
-    Yb = out.clone(); outs.append(out.cpu().numpy().copy()); outs.append(np.float32([rew.item()]))
-assert e.P == 1 or e.exchange == os.environ.get("MBD_EXCHANGE", "p2p"), e.exchange
-if e.sym is not None:
-    assert int(e.xerr.item()) == 0
+Nd = 100
+_, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, Nd)
+e = eng.DiffusionEngine(env, 2048, 50, 0.1, demo, st, Ndiffuse=Nd)
+e.load_schedule(eng.key_chain(np.uint32([3, 1]), Nd), sigmas, alphas, alphas_bar)
+e.set_step(Nd - 1)
+if os.environ.get("MBD_TEST_GRAPH", "1") == "1":
+    e.capture()                      # one captured step, replayed: the cross-GPU rendezvous epochs live on the device
+for _ in range(4):
+    e.step()
+torch.cuda.synchronize()
+e.check_exchange()
+assert e.P == 1 or e.exchange == "p2p", e.exchange
+assert int(e.ctl[0].item()) == Nd - 5
 if e.rank == 0:
-    np.save(os.environ["MBD_OUT"], np.concatenate(outs))
+    np.save(os.environ["MBD_OUT"], np.concatenate([e.Ybars[Nd - 5:Nd - 1].cpu().numpy().reshape(-1), e.rew_hist.cpu().numpy()]))
 if e.P > 1:
     dist.destroy_process_group()
 '''
@@ -58,8 +59,8 @@ def test_two_rank_nccl_equals_single_gpu(tmp_path, demo):
     env1 = dict(env, MBD_OUT=str(tmp_path / "p1.npy"))
     subprocess.run([sys.executable, str(w)], check=True, env=env1, timeout=600)
     a = np.load(tmp_path / "p1.npy")
-    for mode in ("p2p", "nccl"):   # fused NVLink peer-memory gather, and the NCCL all_gather fallback
-        env2 = dict(env, MBD_OUT=str(tmp_path / f"p2_{mode}.npy"), MBD_EXCHANGE=mode)
+    for mode in ("graph", "direct"):   # one captured step replayed / three direct launches per step
+        env2 = dict(env, MBD_OUT=str(tmp_path / f"p2_{mode}.npy"), MBD_TEST_GRAPH="1" if mode == "graph" else "0")
         subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(_port()), str(w)], check=True, env=env2, timeout=600)
         b = np.load(tmp_path / f"p2_{mode}.npy")

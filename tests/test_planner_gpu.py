@@ -91,39 +91,92 @@ def test_std_guard_uniform_weights():
     assert np.allclose(N(w), 1 / n, rtol=1e-6) and N(sc)[1] == 1.0 and np.isclose(N(sc)[0], 0.25)
 
 
+@pytest.mark.parametrize("demo", [False, True], ids=["humanoidrun", "humanoidtrack-demo"])
 @pytest.mark.parametrize("P", [2, 4, 8])
-def test_shard_count_invariance_bit_exact(humanoidrun_setup, P):
-    """Emulates P ranks on one GPU with the same kernels/arguments each rank would use:
-    the combined result equals the single-rank result bit for bit."""
+def test_shard_count_invariance_bit_exact(humanoidrun_setup, P, demo):
+    """P ranks EMULATED on one GPU (one engine + stream per rank, plain device buffers as the peers' symmetric memory): the
+    very kernels of a sharded run — cross-GPU flag rendezvous, peer loads of the returns inside the statistics kernel,
+    peer loads of the rank partials inside the update kernel — give the single-rank result bit for bit, over two
+    consecutive steps (flag epochs, ticket reset, step counter)."""
+    if demo:
+        env = mbd_b200.envs.get_env("humanoidtrack"); st = env.reset(None).pipeline_state.raw
+    else:
+        env, blob, st = humanoidrun_setup
+    Nn, H, temp, Nd = 1024, 50, 0.1, 100
+    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, Nd)
+    keys = eng.key_chain(np.uint32([4, 4]), Nd)
+    e1 = eng.DiffusionEngine(env, Nn, H, temp, demo, st, Ndiffuse=Nd)
+    e1.load_schedule(keys, sigmas, alphas, alphas_bar); e1.set_step(Nd - 1)
+    e1.step(); e1.step()
+    ranks = eng.DiffusionEngine.make_emulated_ranks(env, Nn, H, temp, demo, st, P, Ndiffuse=Nd)
+    for e in ranks:
+        e.load_schedule(keys, sigmas, alphas, alphas_bar); e.set_step(Nd - 1)
+    eng.DiffusionEngine.step_emulated_ranks(ranks)
+    eng.DiffusionEngine.step_emulated_ranks(ranks)
+    torch.cuda.synchronize()
+    for e in ranks:
+        e.check_exchange()
+        assert int(e.ctl[0].item()) == Nd - 3 and int(e.ctl[1].item()) == 2
+        assert_bit_exact(N(e.Ybars[Nd - 3:Nd - 1]), N(e1.Ybars[Nd - 3:Nd - 1]), f"rank {e.rank} of {P}: iterates")
+        assert_bit_exact(N(e.rew_hist), N(e1.rew_hist), "rews.mean() history")
+        assert_bit_exact(N(e.rews_all), N(e1.rews_all), "gathered returns")
+    assert_bit_exact(np.concatenate([N(e.weights) for e in ranks]), N(e1.weights), "softmax weights")
+    assert_bit_exact(np.concatenate([N(e.Y0s) for e in ranks]), N(e1.Y0s), "sampled actions")
+
+
+def test_exchange_timeout_poisons_the_output(humanoidrun_setup, monkeypatch):
+    """a peer that never shows up: the rendezvous times out, ctl.err is set and the step's outputs are NaN — a stale
+    or missing exchange can never be mistaken for a result (k_peer_gather used stale data after a timeout)"""
+    monkeypatch.setenv("MBD_XCHG_TIMEOUT_S", "0.005")
     env, blob, st = humanoidrun_setup
-    Nn, H, temp = 1024, 50, 0.1
+    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 10)
+    ranks = eng.DiffusionEngine.make_emulated_ranks(env, 256, 50, 0.1, False, st, 2, Ndiffuse=10)
+    for e in ranks:
+        e.load_schedule(eng.key_chain(np.uint32([1, 1]), 10), sigmas, alphas, alphas_bar); e.set_step(9)
+    eng.DiffusionEngine.step_emulated_ranks(ranks, ranks=[0])     # rank 1 never launches
+    torch.cuda.synchronize()
+    assert int(ranks[0].ctl[2].item()) == 1 and np.isnan(N(ranks[0].Ybars[8])).all() and np.isnan(N(ranks[0].weights)).all()
+    with pytest.raises(ops.MbdError, match="rendezvous timed out"):
+        ranks[0].check_exchange()
+
+
+def test_step_graph_replay_equals_direct_launches(humanoidrun_setup):
+    """a captured step replayed k times == k direct launches, bit for bit (parameters come from device memory)"""
+    env, blob, st = humanoidrun_setup
+    Nd = 8
+    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, Nd)
+    keys = eng.key_chain(np.uint32([2, 5]), Nd)
+    outs = []
+    for graph in (False, True):
+        e = eng.DiffusionEngine(env, 512, 50, 0.1, False, st, Ndiffuse=Nd)
+        e.load_schedule(keys, sigmas, alphas, alphas_bar); e.set_step(Nd - 1)
+        if graph:
+            e.capture()
+        for _ in range(Nd - 1):
+            e.step()
+        torch.cuda.synchronize()
+        assert int(e.ctl[0].item()) == 0
+        outs.append((N(e.Ybars).copy(), N(e.rew_hist).copy()))
+    assert_bit_exact(outs[0][0], outs[1][0], "iterates"); assert_bit_exact(outs[0][1], outs[1][1], "reward history")
+
+
+def test_step_matches_round1_kernels(humanoidrun_setup):
+    """the fused tail (cluster statistics + last-CTA tree/update) against the separate round-1 kernels, which stay in the
+    ABI for path_integral: same weighted-mean order (bit-exact given equal weights), statistics within 1e-6"""
+    env, blob, st = humanoidrun_setup
+    Nn, H = 2048, 50
     _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 100)
     coef = eng.update_coef(alphas, alphas_bar, 70)
-    key = np.uint32([4, 4]); Ybar_i = torch.zeros(850, device=DEV)
-    e1 = eng.DiffusionEngine(env, Nn, H, temp, False, st)
-    full, _ = e1.reverse_once(key, float(sigmas[70]), Ybar_i, coef)
-    full = N(full).copy()
-    m = env.device_model(torch.device(DEV)); sti = torch.as_tensor(st, device=DEV)
-    nl = Nn // P
-    rews_all = torch.empty(Nn, device=DEV); Ys = []
-    for r in range(P):
-        Y = torch.empty((nl, 850), device=DEV)
-        ops.sample_rollout(m, sti, key, Nn, r * nl, nl, H, float(sigmas[70]), Ybar_i, Y, rews_all[r * nl:(r + 1) * nl])
-        Ys.append(Y)
-    assert_bit_exact(N(rews_all), N(e1.rews_all))
-    partials = torch.empty((P, 850), device=DEV)
-    for r in range(P):
-        w = torch.empty(nl, device=DEV); sc = torch.zeros(4, device=DEV); scratch = torch.empty(Nn, device=DEV)
-        ops.softmax_weights(rews_all, None, r * nl, nl, temp, 0.0, w, sc, scratch)
-        runs = torch.empty(((nl + 63) // 64) * 850, device=DEV)
-        ops.weighted_sum(w, Ys[r], 850, runs, partials[r])
-    out = torch.empty(850, device=DEV)
-    ops.update(partials, P, 850, Ybar_i, coef, out)
-    assert_bit_exact(N(out), full, f"P={P} vs P=1")
-    # the host-side mirror of the rank combine agrees too
-    Yi = Ybar_i * float(coef[0])
-    host = (float(coef[3]) * (Yi + float(coef[2]) * (float(coef[1]) * (-Yi + float(coef[0]) * tree_sum_rows(partials))))) / float(coef[4])
-    assert np.allclose(N(host), full, rtol=1e-6, atol=1e-7)
+    key = np.uint32([4, 4]); Ybar_i = torch.as_tensor((np.random.default_rng(0).normal(size=850) * 0.1).astype(np.float32), device=DEV)
+    e = eng.DiffusionEngine(env, Nn, H, 0.1, False, st)
+    out, rew = e.reverse_once(key, float(sigmas[70]), Ybar_i, coef)
+    w = torch.empty(Nn, device=DEV); sc = torch.zeros(4, device=DEV); scratch = torch.empty(Nn, device=DEV)
+    ops.softmax_weights(e.rews_local, None, 0, Nn, 0.1, 0.0, w, sc, scratch)
+    assert np.allclose(N(w), N(e.weights), rtol=2e-6, atol=1e-12) and np.allclose(N(sc)[:2], N(e.scalars)[:2], rtol=1e-6)
+    runs = torch.empty(((Nn + 63) // 64) * 850, device=DEV); ref = torch.empty(850, device=DEV)
+    nr = ops.weighted_sum_runs(e.weights, e.Y0s, 850, runs)
+    ops.update(runs, nr, 850, Ybar_i, coef, ref)
+    assert_bit_exact(N(out), N(ref), "tree + update")
 
 
 def test_run_diffusion_car2d_matches_oracle_solve(orc, capsys):
@@ -206,37 +259,31 @@ def test_run_path_integral_cli_surface(capsys):
 
 
 @pytest.mark.parametrize("Nn", [2048, 8192])
-def test_single_kernel_step_equals_separate_launches(humanoidrun_setup, Nn, monkeypatch):
-    """mbd_reverse_step (ONE cooperative kernel per diffusion step) is bit-identical to the five-launch path."""
+def test_single_kernel_step_equals_separate_launches(humanoidrun_setup, Nn):
+    """mbd_reverse_step (ONE cooperative kernel per diffusion step, kept in the ABI) is bit-identical to the separate
+    round-1 kernels it replays (mbd_sample_rollout + mbd_softmax_weights + mbd_weighted_sum_runs + mbd_update)."""
     env, blob, st = humanoidrun_setup
     _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 300)
     coef = eng.update_coef(alphas, alphas_bar, 200)
     key = np.uint32([8, 9]); Ybar_i = torch.as_tensor((np.random.default_rng(1).normal(size=850) * 0.1).astype(np.float32), device=DEV)
-    monkeypatch.setenv("MBD_SINGLE_KERNEL", "0")
-    e0 = eng.DiffusionEngine(env, Nn, 50, 0.1, False, st)
-    ref, rew0 = e0.reverse_once(key, float(sigmas[200]), Ybar_i, coef)
-    assert not e0.single_kernel and e0.launches_last_step == 4
-    monkeypatch.setenv("MBD_SINGLE_KERNEL", "1")
-    e1 = eng.DiffusionEngine(env, Nn, 50, 0.1, False, st)
-    out, rew1 = e1.reverse_once(key, float(sigmas[200]), Ybar_i, coef)
-    assert e1.single_kernel and e1.launches_last_step == 1
-    assert_bit_exact(N(e1.rews_local), N(e0.rews_local)); assert_bit_exact(N(e1.Y0s), N(e0.Y0s))
-    assert_bit_exact(N(e1.weights), N(e0.weights), "weights"); assert_bit_exact(N(e1.scalars), N(e0.scalars), "scalars")
-    assert_bit_exact(N(out), N(ref), "Ybar_im1")
-    # second step on the evolved iterate (exercises buffer reuse)
-    out2, _ = e1.reverse_once(np.uint32([1, 1]), float(sigmas[199]), out.clone(), eng.update_coef(alphas, alphas_bar, 199))
-    ref2, _ = e0.reverse_once(np.uint32([1, 1]), float(sigmas[199]), ref.clone(), eng.update_coef(alphas, alphas_bar, 199))
-    assert_bit_exact(N(out2), N(ref2), "second step")
+    m = env.device_model(torch.device(DEV)); sti = torch.as_tensor(st, device=DEV)
+
+    def buffers():
+        return dict(Y=torch.empty((Nn, 850), device=DEV), r=torch.empty(Nn, device=DEV), w=torch.empty(Nn, device=DEV),
+                    sc=torch.zeros(4, device=DEV), runs=torch.empty(((Nn + 63) // 64) * 850, device=DEV), out=torch.empty(850, device=DEV))
+    a, b = buffers(), buffers()
+    ops.sample_rollout(m, sti, key, Nn, 0, Nn, 50, float(sigmas[200]), Ybar_i, a["Y"], a["r"])
+    ops.softmax_weights(a["r"], None, 0, Nn, 0.1, 0.0, a["w"], a["sc"], torch.empty(Nn, device=DEV))
+    ops.update(a["runs"], ops.weighted_sum_runs(a["w"], a["Y"], 850, a["runs"]), 850, Ybar_i, coef, a["out"])
+    assert ops.reverse_step(m, sti, key, Nn, 50, float(sigmas[200]), Ybar_i, 0.1, coef, b["Y"], b["r"], b["w"], b["sc"], b["runs"], b["out"])
+    for k in ("r", "Y", "w", "sc", "out"):
+        assert_bit_exact(N(b[k]), N(a[k]), k)
 
 
-def test_single_kernel_step_falls_back(humanoidrun_setup, monkeypatch):
-    """tiny shards (v1 kernel territory) and the demo branch are not covered: the engine uses the separate launches"""
-    monkeypatch.setenv("MBD_SINGLE_KERNEL", "1")
+def test_single_kernel_step_reports_unsupported(humanoidrun_setup):
+    """tiny shards (v1 kernel territory) are not covered: the entry point says so instead of running something else"""
     env, blob, st = humanoidrun_setup
-    _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, 100)
-    e = eng.DiffusionEngine(env, 256, 50, 0.1, False, st)
-    assert e.single_kernel            # requested ...
-    e.reverse_once(np.uint32([1, 2]), float(sigmas[50]), torch.zeros(850, device=DEV), eng.update_coef(alphas, alphas_bar, 50))
-    assert not e.single_kernel and e.launches_last_step == 4
-    t = mbd_b200.envs.get_env("humanoidtrack")
-    assert not eng.DiffusionEngine(t, 256, 50, 0.1, True, t.reset(None)).single_kernel
+    m = env.device_model(torch.device(DEV)); sti = torch.as_tensor(st, device=DEV)
+    z = lambda *s: torch.zeros(*s, device=DEV)   # noqa: E731
+    assert not ops.reverse_step(m, sti, np.uint32([1, 2]), 256, 50, 0.5, z(850), 0.1, [1, 1, 1, 1, 1], z(256, 850), z(256), z(256), z(4),
+                                z(4 * 850), z(850))
