@@ -103,11 +103,27 @@ class ClockSampler:
 # CPU arm: the oracle port on all host threads
 # ---------------------------------------------------------------------------------------------------------------------
 def _host_threads() -> int:
-    """every hardware thread this process may run on — torchrun exports OMP_NUM_THREADS=1, which round 1 obeyed by accident"""
+    """every hardware thread this process may USE: the affinity mask capped by the cgroup CPU quota (a container can see 128
+    CPUs and be allowed 32 of them; 128 OpenMP threads then only oversubscribe).  torchrun exports OMP_NUM_THREADS=1,
+    which round 1 obeyed by accident — the count is passed to the oracle explicitly."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return max(1, os.cpu_count() or 1)
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except Exception:  # noqa: BLE001
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                q, per = int(f.read()), int(g.read())
+            if q > 0:
+                n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, n)
 
 
 def time_cpu_oracle(n_samples: int, steps: int, warmup: int):
@@ -371,7 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-samples", type=int, default=1024)
+    ap.add_argument("--cpu-samples", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
     args = ap.parse_args()

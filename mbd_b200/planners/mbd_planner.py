@@ -132,7 +132,7 @@ def final_reward(env, engine: DiffusionEngine, us: torch.Tensor) -> float:
     if env.kind == "xpbd":
         out = ops.rollout(engine.model, engine.state_init, us)
     else:
-        out = ops.car2d_rollout(engine.params, engine.state_init, us)
+        out = ops.car2d_rollout(engine.params_car, engine.state_init, us)
     return float(out["rews"][0].item())
 
 
