@@ -32,12 +32,12 @@ int mbd_layout_info(int32_t* out, int n);
 int mbd_abi_sizes(int32_t* out, int n);
 const char* mbd_last_error(void);
 int mbd_device_count(void);
-/* rollout kernel mapping: 0 = auto (by shard size), 1 = v1 (one link per lane), 2/3/4 = v2 (one link per
- * warp, lane = sample) with CTA-wide / named-barrier / mbarrier phase synchronisation, 5 = v2 with two
+/* rollout kernel mapping: 0 = auto (by shard size), 1 = v1 (one link per lane), 2/3 = v2 (one link per
+ * warp, lane = sample) with CTA-wide / named-barrier phase synchronisation (4, mbarrier polling, was removed), 5 = v2 with two
  * same-type links per warp (16 samples per CTA), 6 = v2 with two interleaved 32-sample groups per 704-thread CTA
  * (leaf links decoupled from the group barriers), 8/9 = packed kernel: two samples per lane on FFMA2/FMUL2/FADD2,
  * 64 samples per CTA, group barriers / named edge barriers (11-link models; others fall back to 2), 10 = 6 with
- * neighbourhood barriers (one rendezvous id per parent node).  7 is unused.
+ * neighbourhood barriers (one rendezvous id per parent node), 11 = the packed kernel with them.  4 and 7 are unused.
  * All variants produce bit-identical results; the switch exists for tests and profiling. */
 int mbd_set_kernel_variant(int v);
 /* tuning hook: slot -> link order of the one-link-per-warp mapping (slot L-1 gets the highest warp id) */

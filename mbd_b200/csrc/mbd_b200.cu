@@ -325,15 +325,10 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
   typename std::conditional<GROUPS != 1, typename std::conditional<SYNC == 3, SyncHood, SyncGroup<kGroupLinks>>::type,
-      typename std::conditional<SYNC == 1, SyncP2P, typename std::conditional<SYNC == 2, SyncNamed, SyncCta>::type>::type>::type Y;
+      typename std::conditional<SYNC == 2, SyncNamed, SyncCta>::type>::type Y;
   if constexpr (GROUPS != 1 && SYNC == 3) Y.setup(M, l, L, 1 + 7 * grp, 7);
   if constexpr (GROUPS != 1 && SYNC != 3) { Y.base = 1 + 4 * grp; Y.count_x = a.count_x; }
   if constexpr (SYNC == 2) Y.setup(M, l, L);
-  if constexpr (SYNC == 1) {
-    Y.pose = edge_bars; Y.terms = edge_bars + MBD_MAXL; Y.ph_pose = 0u; Y.ph_terms = 0u;
-    if (tid < 2 * MBD_MAXL) asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_u32(&edge_bars[tid])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   int aid[MBD_MAXDOF];
 #pragma unroll
   for (int k = 0; k < MBD_MAXDOF; ++k) aid[k] = k < c.ndof ? M.li(MBD_F_DOF0 + k * MBD_DOF_STRIDE + MBD_D_ACT, l) : -1;
@@ -1125,7 +1120,7 @@ int mbd_device_count(void) {
 }
 
 int mbd_set_kernel_variant(int v) {
-  if (v < 0 || v > 11 || v == 7) return MBD_EINVAL;
+  if (v < 0 || v > 11 || v == 7 || v == 4) return MBD_EINVAL;   // 4 (mbarrier polling) was removed in round 2
   g_kernel_variant = v;
   return MBD_OK;
 }
@@ -1302,7 +1297,6 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
       } else if (L == 11 && variant == 2) MBD_LAUNCH_WPL(11, 2, 0, 1, grid, 32 * L);       // CTA-wide barriers
       else if (L == 11 && variant == 3 && grid <= 148) MBD_LAUNCH_WPL(11, 1, 2, 1, grid, 32 * L);  // one CTA per SM: no register cap
       else if (L == 11 && variant == 3) MBD_LAUNCH_WPL(11, 2, 2, 1, grid, 32 * L);  // named edge barriers
-      else if (L == 11 && variant == 4) MBD_LAUNCH_WPL(11, 2, 1, 1, grid, 32 * L);  // mbarrier point-to-point
       else MBD_LAUNCH_WPL(MBD_MAXL, 1, 0, 1, grid, 32 * L);
     }
   } else {

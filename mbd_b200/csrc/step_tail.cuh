@@ -221,15 +221,38 @@ __device__ __forceinline__ float tail_tree_rows(const float* const* bases, const
   auto ld = [&](int r) -> float { return PEER ? __ldcv(bases[r] + j) : __ldcg(rows + (size_t)r * stride + j); };
   float stack[32];
   int depth = 0, r = 0;
-  for (; r + 8 <= count; r += 8) {
+  // aligned blocks of 32 rows: 32 loads in flight, folded in registers in adjacent-pair order (5 levels) and pushed at level 5 —
+  // the association of the binary counter, with a quarter of the L2 round trips of the 8-row blocks
+  for (; r + 32 <= count; r += 32) {
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = ld(r + k);
+#pragma unroll
+    for (int w = 1; w < 32; w <<= 1)
+#pragma unroll
+      for (int k = 0; k < 32; k += 2 * w) v[k] = v[k] + v[k + w];
+    float b = v[0];
+    int rr = r >> 5;
+    int lvl = 0;
+    while (rr & 1) { b = stack[--depth] + b; rr >>= 1; ++lvl; }
+    (void)lvl;
+    stack[depth++] = b;
+  }
+  // after the 32-blocks the counter holds one entry per set bit of (r >> 5), all at levels >= 5; the rest (< 32 rows) is
+  // folded by 8-row blocks (level 3) and single rows exactly as before, then merged top-down
+  float sub[4];      // sub-stack of the ragged part, levels 3..4 (at most 3 blocks of 8)
+  int sd = 0;
+  for (int q = 0; r + 8 <= count; r += 8, ++q) {
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = ld(r + k);
     float b = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-    int rr = r >> 3;
-    while (rr & 1) { b = stack[--depth] + b; rr >>= 1; }
-    stack[depth++] = b;
+    int rr = q;
+    while (rr & 1) { b = sub[--sd] + b; rr >>= 1; }
+    sub[sd++] = b;
   }
+  float tail_v = 0.0f;
+  bool has_tail = false;
   if (r < count) {
     float tstack[4];
     int td = 0;
@@ -241,11 +264,16 @@ __device__ __forceinline__ float tail_tree_rows(const float* const* bases, const
     }
     float v = tstack[--td];
     while (td > 0) v = tstack[--td] + v;
-    stack[depth++] = v;
+    tail_v = v;
+    has_tail = true;
   }
-  float v = stack[--depth];
-  while (depth > 0) v = stack[--depth] + v;
-  return v;
+  // merge: ragged singles into the 8-block sub-stack, that into the main stack, then the main stack top-down
+  float acc = 0.0f;
+  bool have = false;
+  if (has_tail) { acc = tail_v; have = true; }
+  while (sd > 0) { float t = sub[--sd]; acc = have ? t + acc : t; have = true; }
+  while (depth > 0) { float t = stack[--depth]; acc = have ? t + acc : t; have = true; }
+  return acc;
 }
 
 // mbd_planner.py:100,130-133 literally (k_update in mbd_b200.cu)
@@ -270,8 +298,26 @@ __global__ void __launch_bounds__(kUpdThreads) k_step_update(TailArgs a) {
     if (j < HNu) {
       const float* __restrict__ w = a.weights;
       const float* __restrict__ Y = a.Y0s;
-      float acc = w[n0] * Y[(size_t)n0 * HNu + j];
-      for (int n = n0 + 1; n < n1; ++n) acc = fmaf(w[n], Y[(size_t)n * HNu + j], acc);
+      float acc;
+      if (n1 - n0 == kTailRun) {
+        // full run: 16 loads in flight per thread (the accumulation order stays sequential)
+        float y[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) y[k] = Y[(size_t)(n0 + k) * HNu + j];
+        acc = w[n0] * y[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) acc = fmaf(w[n0 + k], y[k], acc);
+#pragma unroll
+        for (int b = 16; b < kTailRun; b += 16) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) y[k] = Y[(size_t)(n0 + b + k) * HNu + j];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) acc = fmaf(w[n0 + b + k], y[k], acc);
+        }
+      } else {
+        acc = w[n0] * Y[(size_t)n0 * HNu + j];
+        for (int n = n0 + 1; n < n1; ++n) acc = fmaf(w[n], Y[(size_t)n * HNu + j], acc);
+      }
       a.runs[(size_t)r * HNu + j] = acc;
     }
   }

@@ -89,12 +89,9 @@ __device__ __forceinline__ void axis_angle_1dof(q4 j, float& psi, float& r10, fl
 
 // ---- synchronisation policies --------------------------------------------------------------------
 // SyncCta: four CTA-wide barriers per physics step (simple, any tree).
-// SyncP2P: point-to-point mbarriers along the tree edges — link l owns two mbarriers (count 32):
-//   pose[l]  : l arrives after publishing its pose (phases B, D); its CHILDREN wait on it (A, C)
-//   terms[l] : l arrives after writing its parent-directed terms (A, C); its PARENT waits (B, D)
-// so unrelated limbs never wait for each other and leaves (the shins with their contact work)
-// never hold up anybody but their own parent.  No lapping is possible: a producer's next
-// arrival on either barrier transitively requires its consumers to have passed the wait.
+// (Round 1 also carried an mbarrier-polling edge protocol, "SyncP2P" / kernel variant 4, kept for comparison only: it was
+// slower than the named barriers and compute-sanitizer's synccheck flags its unwaited phases — leaf links arrive on pose
+// barriers that no child ever waits on — so it was removed in round 2 rather than exempted.)
 struct SyncCta {
   __device__ __forceinline__ void wait_pose(int) {}
   __device__ __forceinline__ void arrive_terms(int) {}
@@ -185,46 +182,7 @@ struct SyncHood {
   }
 };
 
-struct SyncP2P {
-  uint64_t* pose;   // [L]
-  uint64_t* terms;  // [L]
-  uint32_t ph_pose, ph_terms;
-  static __device__ __forceinline__ uint32_t a32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-  static __device__ __forceinline__ void arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a32(b)) : "memory");
-  }
-  static __device__ __forceinline__ void wait(uint64_t* b, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(a32(b)), "r"(parity)
-          : "memory");
-    }
-  }
-  __device__ __forceinline__ void wait_pose(int parent) {
-    if (parent >= 0) wait(&pose[parent], ph_pose);
-    ph_pose ^= 1u;
-  }
-  __device__ __forceinline__ void arrive_terms(int l) { arrive(&terms[l]); }
-  __device__ __forceinline__ void wait_terms(const int* child) {
-#pragma unroll
-    for (int k = 0; k < MBD_MAXCHILD; ++k)
-      if (child[k] >= 0) wait(&terms[child[k]], ph_terms);
-    ph_terms ^= 1u;
-  }
-  __device__ __forceinline__ void arrive_pose(int l) { arrive(&pose[l]); }
-  __device__ __forceinline__ void phase_end() {}
-  template <class C> __device__ __forceinline__ void end_A(const C&) {}
-  template <class C> __device__ __forceinline__ void end_B(const C&) {}
-  template <class C> __device__ __forceinline__ void end_C(const C&) {}
-  template <class C> __device__ __forceinline__ void end_D(const C&) {}
-};
-
-// SyncNamed: the same edge protocol on hardware named barriers (bar.arrive / bar.sync, ids 1..15):
+// SyncNamed: a point-to-point protocol along the tree edges on hardware named barriers (bar.arrive / bar.sync, ids 1..15):
 // waiting warps sleep in the barrier unit instead of polling an mbarrier, so they do not steal
 // issue slots from the working warps.  Each node WITH children owns two ids:
 //   pose id : the node bar.arrive's, each child bar.sync's      (count = 32 * (1 + nchildren))
