@@ -36,8 +36,8 @@ int mbd_device_count(void);
  * warp, lane = sample) with CTA-wide / named-barrier phase synchronisation (4, mbarrier polling, was removed), 5 = v2 with two
  * same-type links per warp (16 samples per CTA), 6 = v2 with two interleaved 32-sample groups per 704-thread CTA
  * (leaf links decoupled from the group barriers), 8/9 = packed kernel: two samples per lane on FFMA2/FMUL2/FADD2,
- * 64 samples per CTA, group barriers / named edge barriers (11-link models; others fall back to 2), 10 = 6 with
- * neighbourhood barriers (one rendezvous id per parent node), 11 = the packed kernel with them.  4 and 7 are unused.
+ * 64 samples per CTA, group barriers / named edge barriers (11-link models; others fall back to 2).  4 and 7 are unused
+ * (as are 10 / 11, a round-2 experiment that lost and was removed).
  * All variants produce bit-identical results; the switch exists for tests and profiling. */
 int mbd_set_kernel_variant(int v);
 /* tuning hook: slot -> link order of the one-link-per-warp mapping (slot L-1 gets the highest warp id) */

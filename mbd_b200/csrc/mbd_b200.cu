@@ -269,7 +269,7 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
 
   static_assert(SPLIT == 1 || SPLIT == 2, "links per warp");
   static_assert(SPLIT == 1 || SYNC == 0, "edge barriers assume one link per warp");
-  static_assert(GROUPS == 1 || (SPLIT == 1 && (SYNC == 0 || SYNC == 3)), "sample groups: one link per warp, group or neighbourhood barriers");
+  static_assert(GROUPS == 1 || (SPLIT == 1 && SYNC == 0), "sample groups: one link per warp, group barriers");
   constexpr int kLpl = kWplLanes / SPLIT;                      // lanes (= samples) per link
   const int tid = threadIdx.x, lane = tid & 31;
   // GROUPS independent 32-sample groups share the CTA with their warps INTERLEAVED (warp w -> group w % GROUPS,
@@ -324,10 +324,9 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
     s.v = V3(st[10], st[11], st[12]);
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
-  typename std::conditional<GROUPS != 1, typename std::conditional<SYNC == 3, SyncHood, SyncGroup<kGroupLinks>>::type,
+  typename std::conditional<GROUPS != 1, SyncGroup<kGroupLinks>,
       typename std::conditional<SYNC == 2, SyncNamed, SyncCta>::type>::type Y;
-  if constexpr (GROUPS != 1 && SYNC == 3) Y.setup(M, l, L, 1 + 7 * grp, 7);
-  if constexpr (GROUPS != 1 && SYNC != 3) { Y.base = 1 + 4 * grp; Y.count_x = a.count_x; }
+  if constexpr (GROUPS != 1) { Y.base = 1 + 4 * grp; Y.count_x = a.count_x; }
   if constexpr (SYNC == 2) Y.setup(M, l, L);
   int aid[MBD_MAXDOF];
 #pragma unroll
@@ -523,9 +522,8 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
     s.v = pk::mkV(b(10), b(11), b(12));
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
-  typename std::conditional<SYNC == 2, SyncNamed, typename std::conditional<SYNC == 3, SyncHood, SyncGroup<kPkLinks>>::type>::type Y;
+  typename std::conditional<SYNC == 2, SyncNamed, SyncGroup<kPkLinks>>::type Y;
   if constexpr (SYNC == 2) Y.setup(Ms, l, L);
-  else if constexpr (SYNC == 3) Y.setup(Ms, l, L, 1, 15);
   else { Y.base = 1; Y.count_x = a.count_x; }
   int my_track = -1;
   for (int k = 0; k < ntrack; ++k)
@@ -1120,7 +1118,7 @@ int mbd_device_count(void) {
 }
 
 int mbd_set_kernel_variant(int v) {
-  if (v < 0 || v > 11 || v == 7 || v == 4) return MBD_EINVAL;   // 4 (mbarrier polling) was removed in round 2
+  if (v < 0 || v > 9 || v == 7 || v == 4) return MBD_EINVAL;   // 4 (mbarrier polling) and 10 / 11 (neighbourhood barriers) were removed in round 2
   g_kernel_variant = v;
   return MBD_OK;
 }
@@ -1237,9 +1235,9 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   // named edge barriers; two CTAs per SM (> 148 CTAs) favour plain CTA barriers (better I-cache locality)
   // beyond one 32-sample CTA per SM: two interleaved groups per 704-thread CTA (critical links get the highest warp ids)
   if (variant == 0) variant = (L == 11) ? (a.n < 2048 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 6 : 2))) : 2;
-  if ((variant == 8 || variant == 9 || variant == 11) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
-  if (variant == 8 || variant == 9 || variant == 11) {
-    // packed kernel (11: neighbourhood barriers): 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
+  if ((variant == 8 || variant == 9) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
+  if (variant == 8 || variant == 9) {
+    // packed kernel: 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
     memcpy(a.wl, m->wl1, sizeof(a.wl));
     a.count_x = 32 * (L - m->nlate);
     const int grid = (a.n + mbd::kPkSamples - 1) / mbd::kPkSamples;
@@ -1254,11 +1252,10 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
     if (!pk_attr_set) {
       MBD_PK_ATTR(true, 2, 0); MBD_PK_ATTR(false, 2, 0); MBD_PK_ATTR(true, 2, 2); MBD_PK_ATTR(false, 2, 2);
       MBD_PK_ATTR(true, MBD_MAXCON, 0); MBD_PK_ATTR(false, MBD_MAXCON, 0); MBD_PK_ATTR(true, MBD_MAXCON, 2); MBD_PK_ATTR(false, MBD_MAXCON, 2);
-      MBD_PK_ATTR(true, 2, 3); MBD_PK_ATTR(false, 2, 3); MBD_PK_ATTR(true, MBD_MAXCON, 3); MBD_PK_ATTR(false, MBD_MAXCON, 3);
       pk_attr_set = true;
     }
-    if (m->max_ncon <= 2) { if (variant == 8) MBD_PK_LAUNCH(2, 0); else if (variant == 9) MBD_PK_LAUNCH(2, 2); else MBD_PK_LAUNCH(2, 3); }
-    else { if (variant == 8) MBD_PK_LAUNCH(MBD_MAXCON, 0); else if (variant == 9) MBD_PK_LAUNCH(MBD_MAXCON, 2); else MBD_PK_LAUNCH(MBD_MAXCON, 3); }
+    if (m->max_ncon <= 2) { if (variant == 8) MBD_PK_LAUNCH(2, 0); else MBD_PK_LAUNCH(2, 2); }
+    else { if (variant == 8) MBD_PK_LAUNCH(MBD_MAXCON, 0); else MBD_PK_LAUNCH(MBD_MAXCON, 2); }
 #undef MBD_PK_ATTR
 #undef MBD_PK_LAUNCH
   } else if (variant >= 2) {
@@ -1274,7 +1271,7 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
       else MBD_LAUNCH_WPL(MBD_MAXL, 1, 0, 2, grid, 32 * nw);
     } else {
       int grid = (a.n + mbd::kWplLanes - 1) / mbd::kWplLanes;
-      if (L == 11 && (variant == 6 || variant == 10) && m->max_ncon <= 2) {  // two interleaved 32-sample groups per 704-thread CTA
+      if (L == 11 && variant == 6 && m->max_ncon <= 2) {  // two interleaved 32-sample groups per 704-thread CTA
         int grid2 = (a.n + 63) / 64;
         size_t dyn2 = 2 * dyn;
         memcpy(a.wl, m->wl6, sizeof(a.wl));
@@ -1283,17 +1280,10 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
         if (!attr_set) {
           CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
           CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
-          CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<true, 22, 1, 3, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
-          CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<false, 22, 1, 3, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
           attr_set = true;
         }
-        if (variant == 10) {   // neighbourhood barriers (SyncHood)
-          if (fused) mbd::k_rollout_wpl<true, 22, 1, 3, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
-          else mbd::k_rollout_wpl<false, 22, 1, 3, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
-        } else {
-          if (fused) mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
-          else mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
-        }
+        if (fused) mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
+        else mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2><<<grid2, 64 * L, dyn2, st>>>(a);
       } else if (L == 11 && variant == 2) MBD_LAUNCH_WPL(11, 2, 0, 1, grid, 32 * L);       // CTA-wide barriers
       else if (L == 11 && variant == 3 && grid <= 148) MBD_LAUNCH_WPL(11, 1, 2, 1, grid, 32 * L);  // one CTA per SM: no register cap
       else if (L == 11 && variant == 3) MBD_LAUNCH_WPL(11, 2, 2, 1, grid, 32 * L);  // named edge barriers

@@ -139,49 +139,8 @@ struct SyncGroup {
   }
 };
 
-// SyncHood: neighbourhood barriers.  Every node WITH children owns ONE hardware barrier id; at each of the four phase
-// boundaries the node and all its children rendezvous on it (blocking bar.sync for everybody, so a generation can never
-// receive two arrivals of the same warp).  A link first syncs with its parent's neighbourhood, then with its own: the
-// order follows the tree depth, so there is no cycle of waits.  Every edge's endpoints meet at every boundary, i.e. the
-// protocol is at least as strong as the directed pose / terms protocol of SyncNamed (same hazard analysis), but links
-// that are d edges apart may be d phases apart: sub-trees de-phase and the fp32 pipe sees joint-phase work while other
-// links integrate or solve contacts.  7 ids per humanoid group: two groups fit into the 15 usable ids.
-struct SyncHood {
-  int par, own;   // (id | count << 8) of the parent's / the own neighbourhood, 0 = none
-  static __device__ __forceinline__ void bar_sync(int packed) {
-    asm volatile("bar.sync %0, %1;" ::"r"(packed & 0xff), "r"(packed >> 8) : "memory");
-  }
-  __device__ __forceinline__ void wait_pose(int) {}
-  __device__ __forceinline__ void arrive_terms(int) {}
-  __device__ __forceinline__ void wait_terms(const int*) {}
-  __device__ __forceinline__ void arrive_pose(int) {}
-  __device__ __forceinline__ void meet() {
-    if (par) bar_sync(par);
-    if (own) bar_sync(own);
-  }
-  template <class C> __device__ __forceinline__ void end_A(const C&) { meet(); }
-  template <class C> __device__ __forceinline__ void end_B(const C&) { meet(); }
-  template <class C> __device__ __forceinline__ void end_C(const C&) { meet(); }
-  template <class C> __device__ __forceinline__ void end_D(const C&) { meet(); }
-  // first_id: first barrier id of this group; returns false when the group needs more than max_ids ids
-  __device__ __forceinline__ bool setup(const ModelSmem& M, int l, int L, int first_id, int max_ids) {
-    int nparents = 0, my_idx = -1, par_idx = -1, my_nch = 0, par_nch = 0;
-    const int parent = M.li(MBD_F_PARENT, l);
-    for (int k = 0; k < L; ++k) {
-      int nch = 0;
-      for (int j = 0; j < MBD_MAXCHILD; ++j) nch += M.li(MBD_F_CHILD0 + j, k) >= 0;
-      if (nch > 0) {
-        if (k == l) { my_idx = nparents; my_nch = nch; }
-        if (k == parent) { par_idx = nparents; par_nch = nch; }
-        ++nparents;
-      }
-    }
-    own = my_idx >= 0 ? ((first_id + my_idx) | ((32 * (1 + my_nch)) << 8)) : 0;
-    par = (parent >= 0 && par_idx >= 0) ? ((first_id + par_idx) | ((32 * (1 + par_nch)) << 8)) : 0;
-    return nparents <= max_ids;
-  }
-};
-
+// (Round-2 experiment "SyncHood" — one rendezvous barrier per parent node, kernel variants 10 / 11 — measured 1-10 % slower than
+// SyncGroup and compute-sanitizer's synccheck flags its bar.sync pattern as divergent: removed rather than exempted.)
 // SyncNamed: a point-to-point protocol along the tree edges on hardware named barriers (bar.arrive / bar.sync, ids 1..15):
 // waiting warps sleep in the barrier unit instead of polling an mbarrier, so they do not steal
 // issue slots from the working warps.  Each node WITH children owns two ids:

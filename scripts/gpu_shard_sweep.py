@@ -17,7 +17,7 @@ for n in (256, 512, 1024, 2048, 4096, 8192):
     ops.set_kernel_variant(2)
     ops.sample_rollout(m, st, key, n, 0, n, H, 0.88, Yb, Y0s, rews); torch.cuda.synchronize()
     ref = rews.cpu().numpy().copy()
-    for v in (0, 1, 2, 3, 5, 6, 8, 9, 10, 11):
+    for v in (0, 1, 2, 3, 5, 6, 8, 9):
         try:
             ops.set_kernel_variant(v)
         except Exception:

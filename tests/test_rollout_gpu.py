@@ -33,7 +33,7 @@ def _actions(rng, n, H, nu, scale=0.88):
     return np.clip(rng.normal(size=(n, H, nu)) * scale, -1, 1).astype(np.float32)
 
 
-@pytest.fixture(params=[1, 2, 3, 5, 6, 8, 9, 10, 11], ids=["v1-lane-per-link", "v2-cta-bar", "v2-named-bar", "v2-split2", "v2-two-groups", "pk-group-bar", "pk-named-bar", "v2-two-groups-hood", "pk-hood"])
+@pytest.fixture(params=[1, 2, 3, 5, 6, 8, 9], ids=["v1-lane-per-link", "v2-cta-bar", "v2-named-bar", "v2-split2", "v2-two-groups", "pk-group-bar", "pk-named-bar"])
 def variant(request):
     ops.set_kernel_variant(request.param)
     yield request.param
