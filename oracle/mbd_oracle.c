@@ -38,6 +38,36 @@
 
 #define ORC_API __attribute__((visibility("default")))
 
+/* ---- [restated] choices behind named compile-time switches ------------------------------------------------------
+ * Every place where Brax's exact expression could not be confirmed has a switch; the DEFAULT values are what the CUDA
+ * kernels implement (tests compare against the default build only).  scripts/pin_against_brax.py rebuilds this file
+ * with other values (make -C oracle variant DEFS="-DORC_...=0" OUT=...) and reports which combination reproduces a real
+ * Brax install, substep by substep.  Alternative readings are listed in DESIGN.md section 2. */
+#ifndef ORC_JOINT_PASSIVE_IN_ACCEL /* 1: dof stiffness / damping torques enter joints.acceleration_update next to the motor torque;
+                                      0: motor torque and constraint_ang_damping only (passive dof terms ignored) */
+#define ORC_JOINT_PASSIVE_IN_ACCEL 1
+#endif
+#ifndef ORC_ANG_DAMP_IN_ACCEL      /* 1: - constraint_ang_damping * jd.ang is part of the joint torque; 0: it is not */
+#define ORC_ANG_DAMP_IN_ACCEL 1
+#endif
+#ifndef ORC_EPS                    /* regulariser added to every XPBD denominator (w1 + w2 + eps) */
+#define ORC_EPS 1e-6f
+#endif
+#ifndef ORC_STATIC_FRICTION_MU     /* static-friction test of resolve_position: 1: |dlambda_t| < mu |dlambda|; 0: |dlambda_t| < |dlambda|
+                                      (the form of Brax v1's colliders; identical for the humanoids, whose mu is 1) */
+#define ORC_STATIC_FRICTION_MU 1
+#endif
+#ifndef ORC_SINKING_GATE           /* 1: the normal velocity impulse acts only when the contact was approaching (v_n_old <= 0); 0: always */
+#define ORC_SINKING_GATE 1
+#endif
+#ifndef ORC_CONTACT_MIDPOINT       /* 1: contact position c - n (r + dist/2) (MJX plane_sphere); 0: the sphere's surface point c - n r */
+#define ORC_CONTACT_MIDPOINT 1
+#endif
+#ifndef ORC_EULER_ACOS             /* 0: joint angles from matrix entries with atan2 only; 1: the middle angle as acos(clip(cos)) * sign(sin),
+                                      the line-of-nodes form (libm acosf: oracle-only, never bit-compared) */
+#define ORC_EULER_ACOS 0
+#endif
+
 /* ================================================================================== */
 /* brax/math.py                                                                        */
 /* ================================================================================== */
@@ -158,7 +188,7 @@ static inline void axis_angle_ang(q4 j, float parity, JointAngles* o) {
   o->r20 = 2.0f * fmaf(x, z, -(w * y));
   float psi = mbd_atan2f(-r12, r22);
   float cth = sqrtf(fmaf(r01, r01, r00 * r00));
-  float theta = mbd_atan2f(r02, cth);
+  float theta = ORC_EULER_ACOS ? copysignf(acosf(clampf(cth, -1.0f, 1.0f)), r02) : mbd_atan2f(r02, cth);
   float phi = mbd_atan2f(-r01, r00);
   float ln;
   v3 lon = vnormalize(V3(0.0f, r22, -r12), &ln);
@@ -184,11 +214,11 @@ static inline void contact_position_plane(const Model* m, int l, int ci, float i
   const float radius = LFf(m, base + 3, l), mu = LFf(m, base + 4, l);
   v3 centre = vadd(p, vrotate(LF3(m, base, l), q));
   float dist = centre.z - radius;                                       /* dist = (c - plane).n - r */
-  v3 cp = V3(centre.x, centre.y, centre.z - (radius + 0.5f * dist));    /* pos = c - n (r + dist/2) */
+  v3 cp = V3(centre.x, centre.y, centre.z - (radius + (ORC_CONTACT_MIDPOINT ? 0.5f * dist : 0.0f)));    /* pos = c - n (r + dist/2) */
   int coll = dist < 0.0f;
   v3 r = vsub(cp, p);
   float w = im + fmaf(r.x, r.x, r.y * r.y);                             /* 1/m + |r x n|^2 (identity inertia) */
-  float dl = coll ? (-dist / (w + 1e-6f)) : 0.0f;
+  float dl = coll ? (-dist / (w + ORC_EPS)) : 0.0f;
   dp->z = dp->z + dl * im;
   *dq = qadd(*dq, qscale(vqmul_xy(r.y * dl, -(r.x * dl), q), 0.5f));
   /* static friction: cancel the tangential travel of the contact point since x_i_prev */
@@ -200,8 +230,8 @@ static inline void contact_position_plane(const Model* m, int l, int ci, float i
   float ntx = dx * inv, nty = dy * inv;
   float c1 = -(r.z * nty), c2 = r.z * ntx, c3 = fmaf(r.x, nty, -(r.y * ntx));
   float wt = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
-  float dlt = -ct / (wt + 1e-6f);
-  int stat = coll && (fabsf(dlt) < mu * fabsf(dl));
+  float dlt = -ct / (wt + ORC_EPS);
+  int stat = coll && (fabsf(dlt) < (ORC_STATIC_FRICTION_MU ? mu : 1.0f) * fabsf(dl));
   float mm = stat ? dlt : 0.0f;
   float ptx = ntx * mm, pty = nty * mm;
   dp->x = dp->x + ptx * im;
@@ -223,15 +253,15 @@ static inline void contact_velocity_plane(const Model* m, int l, int ci, float i
   float mag = fr < vtn ? fr : vtn;
   float c1 = -(r.z * tdy), c2 = r.z * tdx, c3 = fmaf(r.x, tdy, -(r.y * tdx));
   float wd = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
-  float kd = 1.0f / (wd + 1e-6f);
+  float kd = 1.0f / (wd + ORC_EPS);
   float pdx = (tdx * -mag) * kd, pdy = (tdy * -mag) * kd;
   v3 rel_old = vadd(v_before, vcross(w_before, r));
   float vn_old = rel_old.z;
   float rest = -m->elasticity * vn_old;                                 /* restitution: min(-e v_n_old, 0) */
   rest = rest < 0.0f ? rest : 0.0f;
   float wn = im + fmaf(r.x, r.x, r.y * r.y);
-  float prz = (-vn + rest) * (1.0f / (wn + 1e-6f));
-  v3 P = V3(pdx, pdy, (vn_old <= 0.0f) ? prz : 0.0f);                   /* "sinking" gate on the normal impulse */
+  float prz = (-vn + rest) * (1.0f / (wn + ORC_EPS));
+  v3 P = V3(pdx, pdy, (!ORC_SINKING_GATE || vn_old <= 0.0f) ? prz : 0.0f);                   /* "sinking" gate on the normal impulse */
   if (dl == 0.0f) P = V3(0, 0, 0);
   *dv = vadd(*dv, vscale(P, im));
   *dw = vadd(*dw, vcross(r, P));
@@ -281,7 +311,7 @@ static void positional_step(const Model* m, Link* s, const float* act) {
     v3 jd = vinv_rotate(vsub(s[l].w, wp), a_p);
     JointAngles ja;
     axis_angle_ang(j, LFf(m, MBD_F_PARITY, l), &ja);
-    v3 tq = vscale(jd, -LFf(m, MBD_F_ANG_DAMP, l));
+    v3 tq = vscale(jd, ORC_ANG_DAMP_IN_ACCEL ? -LFf(m, MBD_F_ANG_DAMP, l) : -0.0f);
     v3 rcw_s = V3(0, 0, 0), d_s = V3(0, 0, 0), va_s = V3(0, 0, 0), Fw = V3(0, 0, 0);
     if (smask) { /* anchor offset and anchor velocity of the child against the (fixed) world anchor RP */
       rcw_s = vrotate(LF3(m, MBD_F_RC, l), s[l].q);
@@ -302,7 +332,7 @@ static void positional_step(const Model* m, Link* s, const float* act) {
         continue;
       }
       float vel = vdot(ja.ax[k], jd);
-      float t = fmaf(-LFf(m, base + MBD_D_DAMP, l), vel, fmaf(-LFf(m, base + MBD_D_STIFF, l), ja.ang[k], tau));
+      float t = ORC_JOINT_PASSIVE_IN_ACCEL ? fmaf(-LFf(m, base + MBD_D_DAMP, l), vel, fmaf(-LFf(m, base + MBD_D_STIFF, l), ja.ang[k], tau)) : tau;
       tq = vfma(ja.ax[k], t, tq);
     }
     T[l] = vrotate(tq, a_p);
@@ -361,7 +391,7 @@ static void positional_step(const Model* m, Link* s, const float* act) {
     v3 crc = vcross(rcw, n), crp = vcross(rpw, n);
     float w_c = im_c + vdot(crc, crc);
     float w_p = fmaf(ii_p, vdot(crp, crp), im_p);
-    float dl = -c / (w_p + w_c + 1e-6f);
+    float dl = -c / (w_p + w_c + ORC_EPS);
     v3 P = vscale(n, dl);
     v3 dp_c = vscale(P, im_c);
     q4 dq_c = qscale(vqmul(vcross(rcw, P), s[l].q), 0.5f);
@@ -395,7 +425,7 @@ static void positional_step(const Model* m, Link* s, const float* act) {
     float th;
     v3 na = vnormalize(dq, &th);
     float nn = vdot(na, na);
-    float dla = -th / (fmaf(ii_p, nn, nn) + 1e-6f);
+    float dla = -th / (fmaf(ii_p, nn, nn) + ORC_EPS);
     v3 Pa = vscale(na, dla);
     q4 dqa_c = qscale(vqmul(Pa, s[l].q), 0.5f);
     q4 dqa_p = qscale(vqmul(Pa, qp), -0.5f * ii_p);
