@@ -116,10 +116,17 @@ def run_diffusion(args: Args, log_every: int = 10, return_trajectory: bool = Fal
         if args.env_name == "car2d":
             _render_car2d(env, state_init, Yi[-1].cpu().numpy(), args, path)
         elif env.kind == "xpbd":
-            # the reference writes rollout.html through brax.io.html (mbd_planner.py:168-178); Brax is not a dependency
-            # here, so the same trajectory (world pose of every link per env step) is written as arrays instead
-            from ..utils import render_us
-            np.savez(f"{path}/rollout_states.npz", **render_us(env.step, env.sys, state_init, Yi[-1].cpu().numpy()))
+            # mbd_planner.py:168-178: rollout.html = brax.io.html.render(sys with opt.timestep = env.dt, rollout).  The same
+            # page (and the JSON document inside it, which vis_diffusion.py / brax.io.html.render_from_json consume) is written
+            # by mbd_b200.io.brax_json; rollout_states.npz keeps the plain arrays
+            from ..io import brax_json
+            from ..utils import rollout_states, trajectory_arrays
+            rollout = rollout_states(env.step, state_init, Yi[-1].cpu().numpy())
+            with open(f"{path}/rollout.html", "w") as f:
+                f.write(brax_json.render(env.sys, rollout, env.dt))
+            with open(f"{path}/rollout.json", "w") as f:
+                f.write(brax_json.dumps(env.sys, rollout, env.dt))
+            np.savez(f"{path}/rollout_states.npz", **trajectory_arrays(env, rollout))
     rew_final = final_reward(env, engine, Yi[-1])
     if return_trajectory:
         return rew_final, Yi

@@ -65,14 +65,24 @@ def trajectory_arrays(env, pipeline_states):
     return dict(pos=pos, rot=rot, q=q, qd=qd, dt=np.float32(env.dt), link_names=np.asarray(list(env.sys.link_names)))
 
 
-def render_us(step_env, sys, state, us):
-    """Mirror of mbd.utils.render_us: steps `us` from `state` and returns the trajectory (initial state first, as the
-    reference's `rollout` list).  The reference turns that list into a Brax HTML page; Brax is not a dependency here,
-    so the trajectory itself is returned (see `trajectory_arrays`, written to results/<env>/rollout_states.npz by the CLI)."""
-    env = _env_of(step_env)
+def rollout_states(step_env, state, us):
+    """the `rollout` list of mbd.utils.render_us (utils.py:23-34) / vis_diffusion.py:115-121: the pipeline state BEFORE each of
+    the H steps (initial state first)"""
     us = np.asarray(us.detach().cpu().numpy() if isinstance(us, torch.Tensor) else us, dtype=np.float32)
     rollout = []
     for i in range(us.shape[0]):
         rollout.append(state.pipeline_state)
         state = step_env(state, us[i])
-    return trajectory_arrays(env, rollout) if env is not None and getattr(env, "kind", None) == "xpbd" else rollout
+    return rollout
+
+
+def render_us(step_env, sys, state, us, dt=None):
+    """Mirror of mbd.utils.render_us: steps `us` from `state` and returns the Brax-visualizer HTML page of the rollout
+    (`brax.io.html.render(sys, rollout)` in the reference; produced here by mbd_b200.io.brax_json without Brax).  For an env
+    without world poses (car2d) the list of states is returned."""
+    env = _env_of(step_env)
+    rollout = rollout_states(step_env, state, us)
+    if env is not None and getattr(env, "kind", None) == "xpbd":
+        from .io import brax_json
+        return brax_json.render(sys, rollout, env.dt if dt is None else dt)
+    return rollout
