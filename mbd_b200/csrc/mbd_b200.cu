@@ -1017,7 +1017,11 @@ static void build_pairing(mbd_model* m, const uint32_t* blob) {
   m->offs1 = 0; m->offs2 = 0; m->nwarps2 = 0;
   m->nlate = 0;
   for (int l = 0; l < L; ++l) m->nlate += (li(MBD_F_CHILD0, l) < 0 && li(MBD_F_NCON, l) > 0 && li(MBD_F_NDOF, l) > 0) ? 1 : 0;
-  for (int w = 0; w < 32; ++w) m->gw2[w] = (signed char)(((w & 1) << 4) | ((w >> 1) & 15));
+  // two-group CTA: warp w -> (group, slot).  Both groups sit on ALL FOUR SM sub-partition schedulers (group = bit 0 xor bit 2
+  // of the warp id) and group 1 starts ~half a substep late (g_group_stagger): the two groups then demand the fp32 pipe in
+  // different phases.  Measured on humanoidrun 8192 x 50 (scripts/gpu_stagger_sweep.py, profiles/r02_experiments.md):
+  // dedicated scheduler pairs 1.386 ms; shared schedulers in lockstep 1.408 ms; shared + 3500..5000 cycles offset 1.353-1.358 ms.
+  for (int w = 0; w < 32; ++w) m->gw2[w] = (signed char)((((w ^ (w >> 2)) & 1) << 4) | ((w >> 1) & 15));
   for (int l = 0; l < MBD_MAXL; ++l) { m->wl1[l][0] = (signed char)(l < L ? l : 0); m->wl1[l][1] = m->wl1[l][0]; m->wl2[l][0] = m->wl2[l][1] = 0; }
   {
     // One link per warp: warps are issued by SM sub-partition (warp id % 4).  Spread the joint work
@@ -1094,7 +1098,7 @@ static void build_pairing(mbd_model* m, const uint32_t* blob) {
     if (!used[a]) add_pair(a, -1);
 }
 
-static int g_group_stagger = 0;   // cycles, see RolloutArgs::stagger
+static int g_group_stagger = 4000;   // cycles group 1 of a two-group CTA waits before its first step (see build_pairing)
 static int g_kernel_variant = 0;  // 0 = auto, 1 = v1 (lane per link), 2..4 = v2 (warp per link; CTA / named / mbarrier sync)
 static thread_local char g_err[256] = "";
 static int set_err(const char* where, cudaError_t e) {
