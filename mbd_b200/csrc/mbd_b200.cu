@@ -107,6 +107,11 @@ struct RolloutArgs {
   // v2 mapping: link owned by (warp, half) and the half-warp offset (in units of 4 lanes) of every link's row
   signed char wl[MBD_MAXL][2];
   unsigned long long offs;
+  // warp-uniform link topology, copied from the blob by the host: read through the constant bank with a warp-uniform
+  // index (the warp id is taken through __shfl_sync(.., 0), which the compiler tracks as uniform), so ndof / parent /
+  // children / contact count live in UNIFORM registers and every branch on them is a uniform branch — no BSSY / BSYNC /
+  // WARPSYNC convergence bookkeeping around code that can never diverge (22 % of the stall samples of the round-1 kernel)
+  struct LinkCfgP { signed char ndof, parent, ncon, smask, child[MBD_MAXCHILD]; } cfg[MBD_MAXL];
   // multi-group CTAs: warp -> (group << 4) | link slot
   signed char gw[32];
   int count_x;             // group barriers: 32 * (links that are not leaves with contacts), see SyncGroup
@@ -272,10 +277,11 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
   static_assert(GROUPS == 1 || (SPLIT == 1 && SYNC == 0), "sample groups: one link per warp, group barriers");
   constexpr int kLpl = kWplLanes / SPLIT;                      // lanes (= samples) per link
   const int tid = threadIdx.x, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // the warp id as a value the compiler knows to be warp-uniform
   // GROUPS independent 32-sample groups share the CTA with their warps INTERLEAVED (warp w -> group w % GROUPS,
   // link slot w / GROUPS), so the links that the mapping marks critical (highest slots) have the highest warp ids
   // of the whole CTA — the SM arbiter issues the highest eligible warp id first.
-  const int gwe = GROUPS == 1 ? (tid >> 5) : a.gw[tid >> 5];
+  const int gwe = GROUPS == 1 ? warp_u : a.gw[warp_u];
   const int grp = GROUPS == 1 ? 0 : (gwe >> 4);
   const int l = a.wl[gwe & 15][SPLIT == 1 ? 0 : lane / kLpl];  // warp (and half) -> link
   const int slot = lane % kLpl;                                // sample index inside the CTA
@@ -309,7 +315,13 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
   const bool owner = (S.off(l) == (lane / kLpl) * kLpl);
   if (!owner) S.offs = (S.offs & ~(0xFull << (4 * l))) | ((unsigned long long)(((lane / kLpl) * kLpl) >> 2) << (4 * l));
   WarpCfg c;
-  load_warp_cfg(M, l, c);
+  if constexpr (SPLIT == 1) {
+    c.l = l; c.ndof = a.cfg[l].ndof; c.parent = a.cfg[l].parent; c.ncon = a.cfg[l].ncon; c.smask = a.cfg[l].smask;
+#pragma unroll
+    for (int k = 0; k < MBD_MAXCHILD; ++k) c.child[k] = a.cfg[l].child[k];
+  } else {
+    load_warp_cfg(M, l, c);   // two links per warp: the topology differs between the half-warps
+  }
 
   const int n_local = (blockIdx.x * GROUPS + grp) * kLpl + slot;
   const bool active = n_local < a.n && owner;
@@ -480,7 +492,8 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
   pk::Model<pk::f2> M;
   M.t = tab;
   M.f = sblob;
-  const int l = a.wl[tid >> 5][0];   // warp -> link (scheduler-balanced order, build_pairing)
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp id, known-uniform to the compiler (see RolloutArgs::cfg)
+  const int l = a.wl[warp_u][0];   // warp -> link (scheduler-balanced order, build_pairing)
   const int L = M.hi(MBD_H_NLINK), nu = M.hi(MBD_H_NU);
   const int HNu = a.H * nu;
   const int nsub = a.nsub_override > 0 ? a.nsub_override : M.hi(MBD_H_NFRAMES);
@@ -504,8 +517,10 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
   S.X = tab + MBD_BLOB_WORDS;
   S.E = S.X + L * pk::kXF * pk::kLanes;
   S.lane = lane;
-  pk::Cfg c;
-  pk::load_cfg(M, l, c);
+  pk::Cfg c;   // topology through the parameter bank: uniform registers, uniform branches
+  c.l = l; c.ndof = a.cfg[l].ndof; c.parent = a.cfg[l].parent; c.ncon = a.cfg[l].ncon;
+#pragma unroll
+  for (int k = 0; k < MBD_MAXCHILD; ++k) c.child[k] = a.cfg[l].child[k];
 
   // lane holds samples 2*lane (low half) and 2*lane + 1 (high half) of the CTA
   const int n0 = blockIdx.x * kPkSamples + 2 * lane;
@@ -1003,6 +1018,7 @@ struct mbd_model {
   int nwarps2;
   signed char gw2[32];  // two-group CTA: warp -> (group << 4) | slot
   int nlate;            // jointed leaf links with contacts (SyncGroup's late leaves)
+  mbd::RolloutArgs::LinkCfgP cfg[MBD_MAXL];   // warp-uniform topology handed to the kernels through the parameter bank
 };
 
 // Pairs links with the same (ndof, #contacts, has-children) signature so that the two halves of a warp run
@@ -1016,6 +1032,14 @@ static void build_pairing(mbd_model* m, const uint32_t* blob) {
   for (int l = 0; l < L; ++l) sig[l] = li(MBD_F_NDOF, l) * 64 + li(MBD_F_NCON, l) * 4 + (li(MBD_F_CHILD0, l) >= 0 ? 1 : 0);
   m->offs1 = 0; m->offs2 = 0; m->nwarps2 = 0;
   m->nlate = 0;
+  for (int l = 0; l < MBD_MAXL; ++l) {
+    const bool live = l < L;
+    m->cfg[l].ndof = (signed char)(live ? li(MBD_F_NDOF, l) : -1);
+    m->cfg[l].parent = (signed char)(live ? li(MBD_F_PARENT, l) : -1);
+    m->cfg[l].ncon = (signed char)(live ? li(MBD_F_NCON, l) : 0);
+    m->cfg[l].smask = (signed char)((live && li(MBD_F_NDOF, l) > 0) ? li(MBD_F_SLIDE, l) : 0);
+    for (int k = 0; k < MBD_MAXCHILD; ++k) m->cfg[l].child[k] = (signed char)(live ? li(MBD_F_CHILD0 + k, l) : -1);
+  }
   for (int l = 0; l < L; ++l) m->nlate += (li(MBD_F_CHILD0, l) < 0 && li(MBD_F_NCON, l) > 0 && li(MBD_F_NDOF, l) > 0) ? 1 : 0;
   // two-group CTA: warp w -> (group, slot).  Both groups sit on ALL FOUR SM sub-partition schedulers (group = bit 0 xor bit 2
   // of the warp id) and group 1 starts ~half a substep late (g_group_stagger): the two groups then demand the fp32 pipe in
@@ -1233,6 +1257,7 @@ int mbd_sample(const uint32_t key[2], int n_total, int n_begin, int n_local, int
 
 static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cudaStream_t st) {
   const int L = m->L;
+  memcpy(a.cfg, m->cfg, sizeof(a.cfg));
   int variant = g_kernel_variant;
   // auto: small shards keep more warps in flight with the lane-per-link kernel; large ones use v2
   // (measured, humanoidrun): < 2048 samples v1 keeps more warps in flight; one CTA per SM favours the
