@@ -1259,11 +1259,13 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   const int L = m->L;
   memcpy(a.cfg, m->cfg, sizeof(a.cfg));
   int variant = g_kernel_variant;
-  // auto: small shards keep more warps in flight with the lane-per-link kernel; large ones use v2
-  // (measured, humanoidrun): < 2048 samples v1 keeps more warps in flight; one CTA per SM favours the
-  // named edge barriers; two CTAs per SM (> 148 CTAs) favour plain CTA barriers (better I-cache locality)
-  // beyond one 32-sample CTA per SM: two interleaved groups per 704-thread CTA (critical links get the highest warp ids)
-  if (variant == 0) variant = (L == 11) ? (a.n < 2048 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 6 : 2))) : 2;
+  // auto (measured on humanoidrun, profiles/r02_shard_sweep.md): the step is latency-bound below one 32-sample CTA per SM
+  // and throughput-bound above.
+  //   n <= 148 * 8   one 8-sample CTA (4 warps, lane per link, no barriers) per SM: shortest dependent chain   -> v1
+  //   n <= 148 * 32  one 32-sample CTA per SM, warp per link, named edge barriers, uncapped registers           -> v3
+  //   larger         64 samples per SM, two per lane on the packed FFMA2 / FMUL2 / FADD2 path (half the issue slots per
+  //                  sample; with the topology in uniform registers it beats the two-group scalar CTA by 8 %)      -> v9
+  if (variant == 0) variant = (L == 11) ? (a.n <= 148 * 8 ? 1 : (a.n <= 148 * 32 ? 3 : 9)) : 2;
   if ((variant == 8 || variant == 9) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
   if (variant == 8 || variant == 9) {
     // packed kernel: 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
