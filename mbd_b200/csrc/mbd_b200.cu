@@ -1265,7 +1265,7 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   //   n <= 148 * 32  one 32-sample CTA per SM, warp per link, named edge barriers, uncapped registers           -> v3
   //   larger         64 samples per SM, two per lane on the packed FFMA2 / FMUL2 / FADD2 path (half the issue slots per
   //                  sample; with the topology in uniform registers it beats the two-group scalar CTA by 8 %)      -> v9
-  if (variant == 0) variant = (L == 11) ? (a.n <= 148 * 8 ? 1 : (a.n <= 148 * 32 ? 3 : 9)) : 2;
+  if (variant == 0) variant = (L == 11) ? (a.n <= 148 * 8 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 9 : 2))) : 2;   // contact-heavy models (humanoidstandup): CTA barriers
   if ((variant == 8 || variant == 9) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
   if (variant == 8 || variant == 9) {
     // packed kernel: 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
@@ -1387,6 +1387,7 @@ int mbd_reverse_step(const mbd_model* m, const float* state_init_dev, const uint
   a.blob = m->blob_dev; a.state_init = state_init_dev; a.Y0s = Y0s_dev; a.n = n; a.H = H; a.rews = rews_dev;
   a.k0 = key[0]; a.k1 = key[1]; a.n_total = n; a.n_begin = 0; a.sigma = sigma; a.Ybar = Ybar_i_dev;
   memcpy(a.wl, m->wl1, sizeof(a.wl));
+  memcpy(a.cfg, m->cfg, sizeof(a.cfg));
   a.offs = m->offs1;
   mbd::StepTail t;
   t.temp = temp; t.Ybar_i = Ybar_i_dev; t.c0 = coef[0]; t.c1 = coef[1]; t.c2 = coef[2]; t.c3 = coef[3]; t.c4 = coef[4];
