@@ -49,7 +49,7 @@ def key_chain(rng_exp, Ndiffuse: int) -> np.ndarray:
     keys = np.zeros((Ndiffuse, 2), np.uint32)
     r = np.asarray(rng_exp, np.uint32)
     for i in range(Ndiffuse - 1, 0, -1):
-        r, k = prng.split(r)
+        r, k = prng.split2(r)
         keys[i] = k
     return keys
 

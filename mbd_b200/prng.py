@@ -58,3 +58,26 @@ def uniform(key, shape, minval=0.0, maxval=1.0) -> np.ndarray:
     unit = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
     lo, hi = np.float32(minval), np.float32(maxval)
     return np.maximum(lo, unit * (hi - lo) + lo).astype(np.float32).reshape(shape)
+
+
+def _threefry_int(k0: int, k1: int, c0: int, c1: int):
+    """threefry2x32 on Python ints (one block) — the key chain of a solve is sequential, and for two-word inputs plain ints are
+    ~10x faster than numpy scalars"""
+    M = 0xFFFFFFFF
+    ks = (k0, k1, k0 ^ k1 ^ 0x1BD11BDA)
+    x0, x1 = (c0 + ks[0]) & M, (c1 + ks[1]) & M
+    for i in range(5):
+        for r in _ROT[i % 2]:
+            x0 = (x0 + x1) & M
+            x1 = (((x1 << r) | (x1 >> (32 - r))) & M) ^ x0
+        x0 = (x0 + ks[(i + 1) % 3]) & M
+        x1 = (x1 + ks[(i + 2) % 3] + i + 1) & M
+    return x0, x1
+
+
+def split2(key):
+    """split(key, 2) for the planner's `rng, Y0s_rng = split(rng)` chain: returns (new_key, sub_key) as uint32[2] arrays"""
+    k0, k1 = int(key[0]), int(key[1])
+    a0, a1 = _threefry_int(k0, k1, 0, 2)     # counters iota(4) split in halves: blocks (0, 2) and (1, 3)
+    b0, b1 = _threefry_int(k0, k1, 1, 3)
+    return np.array([a0, b0], dtype=np.uint32), np.array([a1, b1], dtype=np.uint32)

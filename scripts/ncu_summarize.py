@@ -19,7 +19,7 @@ keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'dr
 stall = [h for h in hdr if 'issue_stalled' in h and 'per_issue_active' in h and 'pcsamp' not in h]
 with open(out_md, "w") as f:
     f.write(f"# ncu --set full — {title}\n\nCommand: `ncu --set full --clock-control none --import-source on -k regex:k_rollout -s 3 -c 1 "
-            f"python bench.py --steps 2 --warmup 3 --no-cpu-baseline` on 1x B200; workload humanoidrun Nsample=8192 Hsample=50 "
+            f"python scripts/gpu_ncu_target.py <env> <nsample> <variant>` (3 warm-up launches skipped) on 1x B200; workload as in the title (humanoidrun Nsample=8192 Hsample=50 unless stated) "
             f"(2,867,200 XPBD substeps per launch).\n\n| metric | value | unit |\n|---|---|---|\n")
     for k in keys:
         if k in d:
