@@ -308,6 +308,8 @@ def run_gpu(args):
     # ---- the whole solve through the reference-facing API (run_mbd.py:20-39 times exactly this call)
     solve = None
     if not args.no_solve:
+        import gc
+        gc.collect()          # the engines of the step measurements (CUDA graphs, symmetric buffers) are torn down HERE, not inside the timed solve
         barrier()
         t0 = time.perf_counter()
         rew_final = run_diffusion(Args(env_name=ENV_NAME, not_render=True), log_every=10 ** 9)
