@@ -212,7 +212,7 @@ def run_gpu(args):
     keys = eng.key_chain(rng_exp, NDIFFUSE)
     HNu = HSAMPLE * NU
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ev = [ops.Event() for _ in range(3)]
+    ev = [ops.Event() for _ in range(4)]   # before | after rollouts | after statistics | after update
 
     def barrier():
         if world > 1:
@@ -230,7 +230,7 @@ def run_gpu(args):
         (step ms, rollout-kernel ms)"""
         h_in = torch.zeros(HNu, dtype=torch.float32).pin_memory()
         h_out = torch.zeros(HNu + 1, dtype=torch.float32).pin_memory()
-        tot, kern = 0.0, 0.0
+        tot, kern, kw = 0.0, 0.0, 0.0
         i = int(e.ctl[0].item())
         if host_io:
             h_in.copy_(e.Ybars[i].cpu())
@@ -244,32 +244,40 @@ def run_gpu(args):
                 h_out[HNu:].copy_(e.rew_hist[i:i + 1], non_blocking=True)
                 ev[2].record()
             else:
-                ops.step_launch_timed(e._plan_c, ev[0], ev[1], ev[2])
+                ops.step_launch_timed(e._plan_c, ev[0], ev[1], ev[3], ev[2])
             ev[2].synchronize()
             if host_io:
                 h_in.copy_(h_out[:HNu])
             if timed:
                 tot += ev[0].elapsed_ms(ev[2])
-                kern += ev[0].elapsed_ms(ev[1])
+                if not host_io:
+                    kern += ev[0].elapsed_ms(ev[1])
+                    kw += ev[1].elapsed_ms(ev[3])
             i -= 1
-        return tot, kern
+        return tot, kern, kw
+
+    breakdown = {}
 
     def measure(n_total):
         """(ms per step, rollout-kernel ms, e2e ms per step, parity_ok or None, engine) for n_total samples over `world` ranks"""
         e = make_engine(n_total)
         chain(e, args.warmup, False, False)
         barrier()
-        tot, kern = chain(e, args.steps, True, False)
+        tot, kern, kw = chain(e, args.steps, True, False)
         barrier()
         chain(e, 1, False, True)
         barrier()
-        e2e, _ = chain(e, args.steps, True, True)
+        e2e, _, _ = chain(e, args.steps, True, True)
         barrier()
         e.check_exchange()
-        t = torch.tensor([tot, kern, e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([tot, kern, e2e, kw], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot, kern, e2e = (float(v) / args.steps for v in t.tolist())
+        tot, kern, e2e, kw = (float(v) / args.steps for v in t.tolist())
+        breakdown.clear()
+        breakdown.update({"rollout_ms": kern, "statistics_ms": kw, "update_ms": tot - kern - kw,
+                          "note": "CUDA events between the three launches of the step, max over ranks; the statistics kernel includes "
+                                  "the cross-GPU rendezvous + NVLink pull of the returns, the update kernel the exchange of the rank partials"})
         parity = None
         if world > 1:
             # rank 0 re-runs the first steps of the same chain UNSHARDED: the sharded iterates must be the same bits
@@ -294,6 +302,7 @@ def run_gpu(args):
         sampler.start()
     n_weak = NSAMPLE * world if args.scaling == "weak" else NSAMPLE
     ms_step, kern_ms, e2e_ms, parity_ok, e = measure(n_weak)
+    weak_breakdown = dict(breakdown)
     clocks = sampler.stop() if rank == 0 else None
     n_local = e.n_local
     del e
@@ -302,7 +311,7 @@ def run_gpu(args):
         s_ms, s_kern, s_e2e, s_par, es = measure(NSAMPLE)
         strong = {"metric": METRIC, "value": NSAMPLE * HSAMPLE / (s_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": s_ms,
                   "kernel_ms": s_kern, "e2e_value": NSAMPLE * HSAMPLE / (s_e2e * 1e-3), "global_samples": NSAMPLE,
-                  "samples_per_gpu": es.n_local, "parity_ok": s_par,
+                  "samples_per_gpu": es.n_local, "parity_ok": s_par, "kernels": dict(breakdown),
                   "note": "BASELINE config 4: humanoidrun Nsample=8192 sample-sharded across the ranks (strong scaling)"}
         del es
     # ---- the whole solve through the reference-facing API (run_mbd.py:20-39 times exactly this call)
@@ -342,6 +351,7 @@ def run_gpu(args):
             "e2e": {"value": n_weak * HSAMPLE / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": HNu * 4,
                     "d2h_bytes_per_step": HNu * 4 + 4},
             "gpu_launches": 3 * args.steps,
+            "kernels": weak_breakdown,
             "roofline": {"bound": "hbm", "kernel": f"{summ.get('kernel', 'k_rollout_wpl<true,...>')} (fused sampling + rollouts)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": summ.get("dram_bytes_per_launch"), "peak_source": peak_src,

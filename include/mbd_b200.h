@@ -181,9 +181,10 @@ typedef struct mbd_step_plan {
   uint64_t timeout_cycles;           /* cross-GPU rendezvous timeout in SM cycles; 0 = default (~20 s) */
 } mbd_step_plan;
 int mbd_step_launch(const mbd_step_plan* plan, mbd_stream s);
-/* the same three launches with CUDA events (mbd_event_create) recorded before (1), between (1) and (2), after (3): lets a
- * caller time the rollout kernel inside the real step on the launching stream (bench.py's roofline) */
-int mbd_step_launch_ev(const mbd_step_plan* plan, void* ev_before, void* ev_mid, void* ev_after, mbd_stream s);
+/* the same three launches with CUDA events (mbd_event_create; NULL = skip) recorded before (1), between (1) and (2), between
+ * (2) and (3), after (3): lets a caller time each kernel inside the real step on the launching stream (bench.py's roofline
+ * and its per-kernel breakdown at every rank count) */
+int mbd_step_launch_ev(const mbd_step_plan* plan, void* ev_before, void* ev_mid, void* ev_mid2, void* ev_after, mbd_stream s);
 void* mbd_event_create(void);
 void mbd_event_destroy(void* ev);
 int mbd_event_record(void* ev, mbd_stream s);

@@ -1475,7 +1475,7 @@ int mbd_peer_gather(const uint64_t* peer_base_ptrs, int P, int rank, size_t src_
 }
 
 // launches (2) and (3) of a step: statistics / softmax (one cluster) and weighted mean + update ("last CTA done")
-static int step_tail_launch(const mbd_step_plan* pl, cudaStream_t st) {
+static int step_tail_launch(const mbd_step_plan* pl, cudaStream_t st, cudaEvent_t ev_mid2 = nullptr) {
   const int HNu = pl->H * pl->nu;
   const bool demo = pl->xref_dev != nullptr;
   mbd::TailArgs t;
@@ -1493,6 +1493,7 @@ static int step_tail_launch(const mbd_step_plan* pl, cudaStream_t st) {
   t.timeout_cycles = pl->timeout_cycles ? pl->timeout_cycles : 40000000000ull;   // ~20 s: a dead peer, not a slow one
   mbd::k_step_weights<<<mbd::kClusterCtas, mbd::kWeightsThreads, 0, st>>>(t);
   CK(cudaGetLastError());
+  if (ev_mid2) CK(cudaEventRecord(ev_mid2, st));
   const int nruns = (pl->n_local + mbd::kTailRun - 1) / mbd::kTailRun;
   dim3 grid(nruns, (HNu + mbd::kUpdThreads - 1) / mbd::kUpdThreads);
   mbd::k_step_update<<<grid, mbd::kUpdThreads, 0, st>>>(t);
@@ -1501,7 +1502,7 @@ static int step_tail_launch(const mbd_step_plan* pl, cudaStream_t st) {
 }
 
 // ---- one diffusion step with device-resident parameters: three launches, CUDA-graph capturable --------------------------
-static int step_launch_impl(const mbd_step_plan* pl, cudaStream_t st, cudaEvent_t ev_mid) {
+static int step_launch_impl(const mbd_step_plan* pl, cudaStream_t st, cudaEvent_t ev_mid, cudaEvent_t ev_mid2 = nullptr) {
   if (!pl || !pl->state_init_dev || !pl->params_dev || !pl->ctl_dev || !pl->Ybars_dev || !pl->Y0s_dev || !pl->rews_dev ||
       !pl->rews_all_dev || !pl->logp_dev || !pl->weights_dev || !pl->runs_dev || !pl->partial_dev || !pl->scalars_dev)
     return MBD_EINVAL;
@@ -1535,17 +1536,17 @@ static int step_launch_impl(const mbd_step_plan* pl, cudaStream_t st, cudaEvent_
     CK(cudaGetLastError());
   }
   if (ev_mid) CK(cudaEventRecord(ev_mid, st));
-  return step_tail_launch(pl, st);
+  return step_tail_launch(pl, st, ev_mid2);
 }
 int mbd_step_launch(const mbd_step_plan* pl, mbd_stream s) { return step_launch_impl(pl, (cudaStream_t)s, nullptr); }
 
 // mbd_step_launch with CUDA events recorded before launch (1), between launch (1) and launch (2), and after launch (3):
 // bench.py times the rollout kernel inside the real step with them (torch.cuda.Event exposes no handle that a C launch
 // sequence could record into; the events come from mbd_event_create)
-int mbd_step_launch_ev(const mbd_step_plan* pl, void* ev_before, void* ev_mid, void* ev_after, mbd_stream s) {
+int mbd_step_launch_ev(const mbd_step_plan* pl, void* ev_before, void* ev_mid, void* ev_mid2, void* ev_after, mbd_stream s) {
   cudaStream_t st = (cudaStream_t)s;
   if (ev_before) CK(cudaEventRecord((cudaEvent_t)ev_before, st));
-  int rc = step_launch_impl(pl, st, (cudaEvent_t)ev_mid);
+  int rc = step_launch_impl(pl, st, (cudaEvent_t)ev_mid, (cudaEvent_t)ev_mid2);
   if (rc != MBD_OK) return rc;
   if (ev_after) CK(cudaEventRecord((cudaEvent_t)ev_after, st));
   return MBD_OK;

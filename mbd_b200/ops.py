@@ -230,6 +230,7 @@ class Event:
         return float(_lib.lib().mbd_event_elapsed_ms(ctypes.c_void_p(self.h), ctypes.c_void_p(later.h)))
 
 
-def step_launch_timed(plan: "_lib.StepPlan", before: Event, mid: Event, after: Event):
-    check(_lib.lib().mbd_step_launch_ev(ctypes.byref(plan), ctypes.c_void_p(before.h), ctypes.c_void_p(mid.h), ctypes.c_void_p(after.h),
-                                         _stream()), "mbd_step_launch_ev")
+def step_launch_timed(plan: "_lib.StepPlan", before: Event, mid: Event, mid2: Event, after: Event):
+    """events: before the rollout kernel | after it | after the statistics kernel | after the update kernel"""
+    check(_lib.lib().mbd_step_launch_ev(ctypes.byref(plan), ctypes.c_void_p(before.h), ctypes.c_void_p(mid.h), ctypes.c_void_p(mid2.h),
+                                         ctypes.c_void_p(after.h), _stream()), "mbd_step_launch_ev")
