@@ -212,6 +212,7 @@ def run_gpu(args):
     keys = eng.key_chain(rng_exp, NDIFFUSE)
     HNu = HSAMPLE * NU
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    align = torch.zeros(1, device=dev)
     ev = [ops.Event() for _ in range(4)]   # before | after rollouts | after statistics | after update
 
     def barrier():
@@ -236,6 +237,12 @@ def run_gpu(args):
             h_in.copy_(e.Ybars[i].cpu())
         for _ in range(nsteps):
             flush.fill_(1)
+            if world > 1:
+                # the untimed 256 MiB flush ends at a different moment on every GPU; without re-alignment that skew is paid
+                # inside the timed step at the first cross-GPU rendezvous (measured: ~80 us at 8 ranks).  A stream-ordered
+                # one-word NCCL all-reduce (no host sync) lines the ranks up again BEFORE the first timed event — in a real
+                # solve there is no flush and the previous step's rendezvous keeps the ranks aligned.
+                dist.all_reduce(align)
             if host_io:   # the reference-facing call with HOST buffers: H2D of the iterate, D2H of result + reward
                 ev[0].record()
                 e.Ybars[i].copy_(h_in, non_blocking=True)
@@ -346,7 +353,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "chain": f"steps i={NDIFFUSE - 1 - args.warmup}..{NDIFFUSE - args.warmup - args.steps} of the real seed-0 chain",
                        "global_samples": n_weak, "samples_per_gpu": n_local, "parallelism": f"sample-shard x{world}",
                        "exchange": "none" if world == 1 else "NVLink peer loads inside the tail kernels (symmetric memory)",
-                       "l2": "flushed between steps (256 MiB memset, untimed)", "substeps_per_s": value * NFRAMES},
+                       "l2": "flushed between steps (256 MiB memset, untimed" + ("; ranks re-aligned after the flush by an untimed stream-ordered NCCL all-reduce)" if world > 1 else ")"), "substeps_per_s": value * NFRAMES},
             "clocks": clocks,
             "e2e": {"value": n_weak * HSAMPLE / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": HNu * 4,
                     "d2h_bytes_per_step": HNu * 4 + 4},
