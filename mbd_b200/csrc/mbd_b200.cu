@@ -1010,6 +1010,7 @@ __global__ void k_peer_gather(PeerArgs a) {
 // C ABI
 // =====================================================================================================
 struct mbd_model {
+  int device;           // the device the blob lives on: launches on another current device are refused
   uint32_t* blob_dev;
   int L, nu, n_frames, ntrack, max_ncon;
   // v2 kernel mappings (host side): one link per warp, and two same-type links per warp
@@ -1213,6 +1214,7 @@ mbd_model* mbd_model_create(const uint32_t* blob_host, size_t nwords) {
   m->L = hi[MBD_H_NLINK]; m->nu = hi[MBD_H_NU]; m->n_frames = hi[MBD_H_NFRAMES]; m->ntrack = hi[MBD_H_NTRACK];
   if (m->L < 1 || m->L > MBD_MAXL || m->ntrack > MBD_MAXTRACK) { delete m; snprintf(g_err, sizeof(g_err), "bad link count"); return nullptr; }
   build_pairing(m, blob_host);
+  if (cudaGetDevice(&m->device) != cudaSuccess) m->device = 0;
   m->max_ncon = 0;
   for (int l = 0; l < m->L; ++l) { int nc = hi[MBD_HDR_WORDS + MBD_F_NCON * MBD_MAXL + l]; if (nc > m->max_ncon) m->max_ncon = nc; }
   if (m->max_ncon > MBD_MAXCON) { delete m; snprintf(g_err, sizeof(g_err), "too many contacts on one link"); return nullptr; }
@@ -1255,8 +1257,23 @@ int mbd_sample(const uint32_t key[2], int n_total, int n_begin, int n_local, int
     else MBD_LAUNCH_WPL_C(NW, MINB, SYNC, SPLIT, MBD_MAXCON, GRID, THREADS);                           \
   } while (0)
 
+// cudaFuncSetAttribute and occupancy are PER DEVICE: one process may drive several GPUs (PipelineEnv.device_model caches a
+// model per device), so the "already done" flags are kept per device ordinal
+static int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
+
 static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cudaStream_t st) {
   const int L = m->L;
+  {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != m->device) {
+      snprintf(g_err, sizeof(g_err), "model lives on device %d but the current device is %d", m->device, dev);
+      return MBD_EINVAL;
+    }
+  }
   memcpy(a.cfg, m->cfg, sizeof(a.cfg));
   int variant = g_kernel_variant;
   // auto (measured on humanoidrun, profiles/r02_shard_sweep.md): the step is latency-bound below one 32-sample CTA per SM
@@ -1279,7 +1296,8 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
     if (fused) mbd::k_rollout_pk<true, C, S><<<grid, 32 * mbd::kPkLinks, dyn, st>>>(a);         \
     else mbd::k_rollout_pk<false, C, S><<<grid, 32 * mbd::kPkLinks, dyn, st>>>(a);              \
   } while (0)
-    static bool pk_attr_set = false;
+    static bool pk_attr_set_dev[64] = {false};
+    bool& pk_attr_set = pk_attr_set_dev[current_device_slot()];
     if (!pk_attr_set) {
       MBD_PK_ATTR(true, 2, 0); MBD_PK_ATTR(false, 2, 0); MBD_PK_ATTR(true, 2, 2); MBD_PK_ATTR(false, 2, 2);
       MBD_PK_ATTR(true, MBD_MAXCON, 0); MBD_PK_ATTR(false, MBD_MAXCON, 0); MBD_PK_ATTR(true, MBD_MAXCON, 2); MBD_PK_ATTR(false, MBD_MAXCON, 2);
@@ -1307,7 +1325,8 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
         size_t dyn2 = 2 * dyn;
         memcpy(a.wl, m->wl6, sizeof(a.wl));
         a.stagger = g_group_stagger;
-        static bool attr_set = false;
+        static bool attr_set_dev[64] = {false};
+        bool& attr_set = attr_set_dev[current_device_slot()];
         if (!attr_set) {
           CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<true, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
           CK(cudaFuncSetAttribute(mbd::k_rollout_wpl<false, 22, 1, 0, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
@@ -1373,7 +1392,10 @@ int mbd_reverse_step(const mbd_model* m, const float* state_init_dev, const uint
   if (m->L != 11 || m->max_ncon > 2 || g_kernel_variant == 1) return MBD_EUNSUPPORTED;
   const int grid = (n + mbd::kWplLanes - 1) / mbd::kWplLanes;
   const size_t dyn = (size_t)m->L * (mbd::kXF + mbd::kEF) * mbd::kWplLanes * sizeof(float);
-  static int max_coresident = -1;
+  static int max_coresident_dev[64];
+  static bool max_coresident_init = false;
+  if (!max_coresident_init) { for (int i = 0; i < 64; ++i) max_coresident_dev[i] = -1; max_coresident_init = true; }
+  int& max_coresident = max_coresident_dev[current_device_slot()];
   if (max_coresident < 0) {
     int per_sm = 0, dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));

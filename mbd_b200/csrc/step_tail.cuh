@@ -158,10 +158,27 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kWeightsT
     cl.sync();
     ok = cl.map_shared_rank(&s_ok, 0)[0] != 0;
     const int nl = a.n_local;
-    for (int i = g; i < N; i += G) {
-      const int r = i / nl, j = i - r * nl;
-      a.rews_all[i] = ok ? __ldcv(a.peer[r] + a.off_rews + j) : __int_as_float(0x7fc00000);
-      if (a.demo) a.logpd_all[i] = ok ? __ldcv(a.peer[r] + a.off_logpd + j) : __int_as_float(0x7fc00000);
+    // eight NVLink loads in flight per thread (one round trip for the 65,536 returns of an 8 x 8192 run instead of eight)
+    for (int i0 = g; i0 < N; i0 += 8 * G) {
+      float vr[8], vl[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * G;
+        const int r = i < N ? i / nl : 0, j = i < N ? i - r * nl : 0;
+        float* base = a.peer[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) base = (r == q) ? a.peer[q] : base;    // select instead of a dynamically indexed parameter array
+        vr[k] = (ok && i < N) ? __ldcv(base + a.off_rews + j) : __int_as_float(0x7fc00000);
+        vl[k] = (ok && i < N && a.demo) ? __ldcv(base + a.off_logpd + j) : __int_as_float(0x7fc00000);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * G;
+        if (i < N) {
+          a.rews_all[i] = vr[k];
+          if (a.demo) a.logpd_all[i] = vl[k];
+        }
+      }
     }
     if (!ok && g == 0) a.ctl->err = 1u;
   }
