@@ -1,4 +1,5 @@
-"""env-steps/s of one diffusion step for every BASELINE.json config this repo can run (1 GPU), with the
+"""env-steps/s of one diffusion step (mean over 20 consecutive steps of the chain, captured-graph replay) for every BASELINE.json config and
+every other positional env (1 GPU), with the
 per-sample returns of the first 32 samples checked bit for bit against the CPU oracle."""
 import os, sys, json
 import numpy as np, torch
@@ -18,18 +19,19 @@ for name, N, H, demo, Nd in CONFIGS:
     rng, rr = prng.split(prng.PRNGKey(0))
     st = env.reset(rr)
     _, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, Nd)
-    e = eng.DiffusionEngine(env, N, H, 0.1, demo, st)
+    e = eng.DiffusionEngine(env, N, H, 0.1, demo, st, Ndiffuse=Nd)
     Nu = env.action_size
-    Yb = torch.zeros(H * Nu, device="cuda:0"); out = torch.empty(H * Nu, device="cuda:0")
-    key = np.uint32([5, 7]); i = Nd - 1
+    e.load_schedule(eng.key_chain(np.uint32([5, 7]), Nd), sigmas, alphas, alphas_bar)
+    e.set_step(Nd - 1)
+    e.capture()                          # the product path: one captured step (three launches), replayed
+    K = 20
     for _ in range(3):
-        e.reverse_once(key, float(sigmas[i]), Yb, eng.update_coef(alphas, alphas_bar, i), out=out)
+        e.step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    K = 20
     e0.record()
     for _ in range(K):
-        e.reverse_once(key, float(sigmas[i]), Yb, eng.update_coef(alphas, alphas_bar, i), out=out)
+        e.step()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
     Y = e.Y0s[:32].cpu().numpy().reshape(32, H, Nu)
