@@ -64,3 +64,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "mbd_oracle" not in txt.replace("oracle/mbd_oracle.c", ""), os.path.join(dp, f)
+
+
+def test_step_structs_match_the_ctypes_mirrors():
+    """mbd_step_params / mbd_step_ctl / mbd_step_plan cross the ABI by pointer: sizeof and key offsets of the C structs
+    (mbd_abi_sizes) equal those of the ctypes mirrors in mbd_b200/_lib.py"""
+    import ctypes
+    out = np.zeros(16, np.int32)
+    n = _lib.lib().mbd_abi_sizes(out.ctypes.data_as(_lib.c_i32p), 16)
+    P = _lib.StepPlan
+    exp = [ctypes.sizeof(_lib.StepParams), 4 * _lib.STEP_CTL_WORDS, ctypes.sizeof(P), P.n_total.offset, P.xref_dev.offset, P.Y0s_dev.offset,
+           P.P.offset, P.peer_base_ptrs.offset, P.timeout_cycles.offset, 16]
+    assert n == len(exp) and out[:n].tolist() == exp
+    assert ctypes.sizeof(_lib.StepParams) == 4 * _lib.STEP_PARAMS_WORDS == 32
