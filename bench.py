@@ -135,6 +135,7 @@ def time_cpu_oracle(n_samples: int, steps: int, warmup: int):
     from oracle import oracle as orc
     from oracle import planner as opl
     native = orc.use_native()
+    simd = orc.use_simd() is not None     # SIMD across samples (what XLA-CPU under vmap would do); scalar fallback if it cannot be built here
     env = mbd_b200.envs.get_env(ENV_NAME)
     rng, rng_reset = prng.split(prng.PRNGKey(0))
     q = env.sys.init_q.astype(np.float32)
@@ -143,7 +144,7 @@ def time_cpu_oracle(n_samples: int, steps: int, warmup: int):
                            prng.uniform(r2, (env.sys.qd_size(),), minval=-0.01, maxval=0.01)).raw
     key, _ = prng.split(rng)
     _, alphas, alphas_bar, sigmas = opl.make_schedule(1e-4, 1e-2, NDIFFUSE)
-    oenv = opl.OracleEnv("xpbd", NU, blob=env.blob, state=st)
+    oenv = opl.OracleEnv("xpbd", NU, blob=env.blob, state=st, simd=simd)
     threads = _host_threads()
     Yb = np.zeros(HSAMPLE * NU, np.float32)
     times = []
@@ -158,7 +159,9 @@ def time_cpu_oracle(n_samples: int, steps: int, warmup: int):
         if it >= max(warmup, 3):
             times.append(dt)
     t = float(np.median(times))
-    return n_samples * HSAMPLE / t, t, threads, ("-O2 -march=native" if native else "-O2 -mavx2 -mfma")
+    how = (f"{orc.use_simd().orc_simd_width()}-lane SIMD across samples (g++ -O3 -march=native; the templated physics of csrc/xpbd_pk.cuh on a host "
+           "lane type, bit-identical to the scalar C oracle)") if simd else ("scalar C oracle, " + ("-O2 -march=native" if native else "-O2 -mavx2 -mfma"))
+    return n_samples * HSAMPLE / t, t, threads, how
 
 
 def run_reference(args):
@@ -174,8 +177,8 @@ def run_reference(args):
         "warmup": max(args.warmup, 3), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD,
-                   "note": f"CPU restatement (JAX/Brax unavailable): C oracle ({flags}, scalar, one rollout per OpenMP iteration), "
-                           f"{threads} threads, median of {args.steps} steps; each step = a bounded sample of {n} of the {NSAMPLE} rollouts"},
+                   "note": f"CPU restatement (JAX/Brax unavailable): {flags}; OpenMP over {threads} threads, median of {args.steps} steps; "
+                           f"each step = sampling + a bounded sample of {n} of the {NSAMPLE} rollouts + statistics"},
         "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{n} of {NSAMPLE} rollouts x {HSAMPLE} env steps per step, median of {args.steps} steps after "
                                    f"{max(args.warmup, 3)} warm-ups"},
@@ -393,7 +396,7 @@ def run_gpu(args):
             val, tcpu, threads, flags = time_cpu_oracle(args.cpu_samples, 5, 3)
             line["cpu_baseline"] = {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_samples} of {NSAMPLE} rollouts x {HSAMPLE} env steps per step, median of 5 steps "
-                                              f"after 3 warm-ups (CPU restatement, {flags}; JAX/Brax unavailable)"}
+                                              f"after 3 warm-ups (CPU restatement: {flags}; JAX/Brax unavailable)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

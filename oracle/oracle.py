@@ -55,6 +55,55 @@ def use_native() -> bool:
         return False
 
 
+_SIMD = None
+
+
+def use_simd():
+    """Builds (on THIS host, -march=native) and loads oracle/libmbd_oracle_simd.so — the SIMD-across-samples CPU arm of
+    bench.py (mbd_oracle_simd.cpp: the templated physics of csrc/xpbd_pk.cuh instantiated with a 16-lane host type; same
+    bits as the scalar oracle).  Returns the library or None when it cannot be built."""
+    global _SIMD
+    if _SIMD is not None:
+        return _SIMD or None
+    import fcntl
+    root = os.path.join(_HERE, "..")
+    so = os.path.join(_HERE, "libmbd_oracle_simd.so")
+    flags = ["-O3", "-march=native", "-std=c++17", "-ffp-contract=off", "-fno-math-errno", "-fopenmp", "-shared", "-fPIC", "-fvisibility=hidden"]
+    try:
+        with open("/proc/cpuinfo") as f:
+            if "avx512f" in f.read():
+                flags.append("-mprefer-vector-width=512")   # gcc splits 512-bit vectors in two by default on most Xeons: 6x slower here
+    except OSError:
+        pass
+    try:
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            subprocess.run(["g++"] + flags + ["-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "mbd_b200", "csrc"),
+                                              os.path.join(_HERE, "mbd_oracle_simd.cpp"), "-o", so], check=True, capture_output=True)
+        _SIMD = ctypes.CDLL(so)
+    except Exception:  # noqa: BLE001
+        _SIMD = False
+    return _SIMD or None
+
+
+def simd_rollout(blob, state_init, Y0s, want_final=False, nthreads=0):
+    """vmap(rollout_us) through the SIMD CPU arm (humanoidrun / humanoidstandup); None when it does not cover the model"""
+    L_ = use_simd()
+    if L_ is None:
+        return None
+    blob = np.ascontiguousarray(blob, dtype=np.uint32)
+    nl = int(blob.view(np.int32)[1])
+    state_init = np.ascontiguousarray(state_init, dtype=np.float32).reshape(nl, 13)
+    Y0s = np.ascontiguousarray(Y0s, dtype=np.float32)
+    n, H, _ = Y0s.shape
+    rews = np.zeros(n, dtype=np.float32)
+    final = np.zeros((n, nl, 13), dtype=np.float32) if want_final else None
+    rc = L_.orc_simd_rollout(_up(blob), _fp(state_init), _fp(Y0s), n, H, _fp(rews), _fp(final), nthreads)
+    if rc != 0:
+        return None
+    return dict(rews=rews, final=final, logpd=None, rewss=None, track=None)
+
+
 def lib():
     global _LIB
     if _LIB is None:

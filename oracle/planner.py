@@ -67,6 +67,10 @@ class OracleEnv:
     def rollout(self, Y0s, H, xref=None, nthreads=0):
         n = Y0s.shape[0]
         Y = Y0s.reshape(n, H, self.Nu)
+        if self.kind == "xpbd" and self.kw.get("simd") and xref is None:
+            out = orc.simd_rollout(self.kw["blob"], self.kw["state"], Y, nthreads=nthreads)   # SIMD across samples, same bits
+            if out is not None:
+                return out
         if self.kind == "xpbd":
             return orc.xpbd_rollout(self.kw["blob"], self.kw["state"], Y, xref=xref, nthreads=nthreads)
         return orc.car2d_rollout(self.kw["params"], self.kw["x0"], Y, xref=xref, nthreads=nthreads)

@@ -111,3 +111,19 @@ def test_algorithmic_operation_count(harness):
     flop = mul + add + 2 * fma + div + rcp + sqrt
     assert 9000 < flop < 9700                             # 9.34 kFLOP per sample and substep (2296 mul, 799 add, 3024 fma)
     assert 190 <= div + rcp + sqrt <= 200                 # 64 div + 62 rcp + 68 sqrt: the contact-free part is data independent
+
+
+def test_simd_cpu_arm_matches_the_scalar_oracle():
+    """oracle/mbd_oracle_simd.cpp (bench.py's timed CPU arm: the same templated physics on a 16-lane host type, OpenMP over lane
+    groups) gives the scalar C oracle's returns and final states bit for bit, ragged tail group included"""
+    if orc.use_simd() is None:
+        pytest.skip("the SIMD arm does not build on this host")
+    for env_name, n, H in (("humanoidrun", 37, 9), ("humanoidstandup", 19, 6)):
+        env, state, Y0s = _case(env_name, n, H, seed=5)
+        ref = orc.xpbd_rollout(env.blob, state, Y0s, want_final=True)
+        out = orc.simd_rollout(env.blob, state, Y0s, want_final=True, nthreads=3)
+        assert out is not None
+        assert np.array_equal(out["rews"].view(np.uint32), ref["rews"].view(np.uint32))
+        assert np.array_equal(out["final"].view(np.uint32), ref["final"].view(np.uint32))
+    hop = mbd_b200.envs.get_env("hopper")   # slide dofs / other rewards are not covered: the caller falls back to the scalar oracle
+    assert orc.simd_rollout(hop.blob, hop.pipeline_init(hop.sys.init_q, np.zeros(6)).raw, np.zeros((4, 2, 3), np.float32)) is None
