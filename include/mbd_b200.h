@@ -40,6 +40,10 @@ int mbd_device_count(void);
  * (as are 10 / 11, a round-2 experiment that lost and was removed).
  * All variants produce bit-identical results; the switch exists for tests and profiling. */
 int mbd_set_kernel_variant(int v);
+/* threefry counter layout of every in-kernel sampler (process-wide): 0 = legacy (jax_threefry_partitionable=False, what the JAX
+ * known-answer vectors in tests/test_prng.py pin), 1 = partitionable (the default of JAX >= 0.5; [jax-recalled], unpinned).
+ * The host-side key chain must use the same layout (mbd_b200.prng.set_layout). */
+int mbd_set_prng_layout(int partitionable);
 /* tuning hook: slot -> link order of the one-link-per-warp mapping (slot L-1 gets the highest warp id) */
 int mbd_model_set_warp_order(mbd_model* m, const int* order, int n);
 /* tuning hook: cycles the second sample group of a two-group CTA waits before its first step (de-phases the groups) */

@@ -104,6 +104,7 @@ struct RolloutArgs {
   const mbd_step_params* sp;
   const mbd_step_ctl* ctl;
   const float* Ybars;
+  int prng_part;           // 1: partitionable threefry layout (mbd_set_prng_layout), 0: legacy
   // v2 mapping: link owned by (warp, half) and the half-warp offset (in units of 4 lanes) of every link's row
   signed char wl[MBD_MAXL][2];
   unsigned long long offs;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(kRolloutThreads) k_rollout(RolloutArgs a) {
 
   if (FUSED) {
     // each CTA draws the noise of exactly its own samples, then reads it back after the barrier
-    const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+    const uint32_t total = a.prng_part ? 0u : (uint32_t)a.n_total * (uint32_t)HNu;   // 0 selects the partitionable layout
     const SampleParams sq = sample_params(a, HNu);
     const int first = blockIdx.x * kSPB;
     const int cnt = min(kSPB, a.n - first) * HNu;
@@ -293,7 +294,7 @@ __device__ __forceinline__ void rollout_wpl_body(const RolloutArgs& a, float* sb
   const int nthreads = blockDim.x;
 
   if (FUSED) {
-    const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+    const uint32_t total = a.prng_part ? 0u : (uint32_t)a.n_total * (uint32_t)HNu;   // 0 selects the partitionable layout
     const SampleParams sq = sample_params(a, HNu);
     const int first = blockIdx.x * kLpl * GROUPS;
     const int cnt = min(kLpl * GROUPS, a.n - first) * HNu;
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
   const int ntrack = M.hi(MBD_H_NTRACK);
 
   if (FUSED) {
-    const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+    const uint32_t total = a.prng_part ? 0u : (uint32_t)a.n_total * (uint32_t)HNu;   // 0 selects the partitionable layout
     const SampleParams sq = sample_params(a, HNu);
     const int first = blockIdx.x * kPkSamples;
     const int cnt = min(kPkSamples, a.n - first) * HNu;
@@ -658,6 +659,7 @@ struct CarArgs {
   float* rewss; float* rews; const float* xref; int href; float* logpd; float* traj;
   int fused; uint32_t k0, k1; int n_total, n_begin; float sigma; const float* Ybar;
   const mbd_step_params* sp; const mbd_step_ctl* ctl; const float* Ybars;   // device-resident step parameters (see RolloutArgs)
+  int prng_part;
 };
 __global__ void k_car2d(CarArgs a) {
   __shared__ float sp[2 * kCarObs + 4];
@@ -667,7 +669,7 @@ __global__ void k_car2d(CarArgs a) {
   if (i >= a.n) return;
   const float orad = sp[2 * kCarObs], dt = sp[2 * kCarObs + 1], hdt = sp[2 * kCarObs + 2], sdt = sp[2 * kCarObs + 3];
   const int HNu = a.H * 2;
-  const uint32_t total = (uint32_t)a.n_total * (uint32_t)HNu;
+  const uint32_t total = a.prng_part ? 0u : (uint32_t)a.n_total * (uint32_t)HNu;   // 0 selects the partitionable layout
   uint32_t ck0 = a.k0, ck1 = a.k1; float csigma = a.sigma; const float* cYbar = a.Ybar;
   if (a.sp != nullptr) {
     const int si = a.ctl->i;
@@ -1124,6 +1126,7 @@ static void build_pairing(mbd_model* m, const uint32_t* blob) {
 }
 
 static int g_group_stagger = 4000;   // cycles group 1 of a two-group CTA waits before its first step (see build_pairing)
+static int g_prng_part = 0;       // threefry layout of the samplers: 0 legacy, 1 partitionable (mbd_set_prng_layout)
 static int g_kernel_variant = 0;  // 0 = auto, 1 = v1 (lane per link), 2..4 = v2 (warp per link; CTA / named / mbarrier sync)
 static thread_local char g_err[256] = "";
 static int set_err(const char* where, cudaError_t e) {
@@ -1144,6 +1147,11 @@ int mbd_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   return n;
+}
+
+int mbd_set_prng_layout(int partitionable) {
+  g_prng_part = partitionable ? 1 : 0;
+  return MBD_OK;
 }
 
 int mbd_set_kernel_variant(int v) {
@@ -1237,7 +1245,7 @@ int mbd_sample(const uint32_t key[2], int n_total, int n_begin, int n_local, int
   if (!key || n_local <= 0 || HNu <= 0 || n_begin < 0 || n_begin + n_local > n_total) return MBD_EINVAL;
   if ((uint64_t)n_total * (uint64_t)HNu >= 0xffffffffull) return MBD_EINVAL;
   uint32_t count = (uint32_t)n_local * (uint32_t)HNu;
-  mbd::k_sample<<<(count + 255) / 256, 256, 0, (cudaStream_t)s>>>(key[0], key[1], (uint32_t)n_total * (uint32_t)HNu,
+  mbd::k_sample<<<(count + 255) / 256, 256, 0, (cudaStream_t)s>>>(key[0], key[1], g_prng_part ? 0u : (uint32_t)n_total * (uint32_t)HNu,
                                                                 (uint32_t)n_begin * (uint32_t)HNu, count, HNu, sigma, Ybar_dev, Y0s_dev);
   CK(cudaGetLastError());
   return MBD_OK;
@@ -1275,6 +1283,7 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
     }
   }
   memcpy(a.cfg, m->cfg, sizeof(a.cfg));
+  a.prng_part = g_prng_part;
   int variant = g_kernel_variant;
   // auto (measured on humanoidrun, profiles/r02_shard_sweep.md): the step is latency-bound below one 32-sample CTA per SM
   // and throughput-bound above.
@@ -1410,6 +1419,7 @@ int mbd_reverse_step(const mbd_model* m, const float* state_init_dev, const uint
   a.k0 = key[0]; a.k1 = key[1]; a.n_total = n; a.n_begin = 0; a.sigma = sigma; a.Ybar = Ybar_i_dev;
   memcpy(a.wl, m->wl1, sizeof(a.wl));
   memcpy(a.cfg, m->cfg, sizeof(a.cfg));
+  a.prng_part = g_prng_part;
   a.offs = m->offs1;
   mbd::StepTail t;
   t.temp = temp; t.Ybar_i = Ybar_i_dev; t.c0 = coef[0]; t.c1 = coef[1]; t.c2 = coef[2]; t.c3 = coef[3]; t.c4 = coef[4];
@@ -1429,6 +1439,7 @@ int mbd_car2d_rollout(const float* params_dev, const float* x0_dev, const uint32
   a.params = params_dev; a.x0 = x0_dev; a.Y0s = Y0s_dev; a.n = n_local; a.H = H; a.rewss = rewss_dev; a.rews = rews_dev;
   a.xref = xref_dev; a.href = href; a.logpd = logpd_dev; a.traj = traj_dev;
   a.fused = key != nullptr;
+  a.prng_part = g_prng_part;
   if (key) { a.k0 = key[0]; a.k1 = key[1]; a.n_total = n_total; a.n_begin = n_begin; a.sigma = sigma; a.Ybar = Ybar_dev; }
   mbd::k_car2d<<<(n_local + 63) / 64, 64, 0, (cudaStream_t)s>>>(a);
   CK(cudaGetLastError());
@@ -1552,7 +1563,7 @@ static int step_launch_impl(const mbd_step_plan* pl, cudaStream_t st, cudaEvent_
     memset(&a, 0, sizeof(a));
     a.params = pl->car_params_dev; a.x0 = pl->state_init_dev; a.Y0s = pl->Y0s_dev; a.n = pl->n_local; a.H = pl->H;
     a.rews = pl->rews_dev; a.xref = pl->xref_dev; a.href = pl->href; a.logpd = demo ? pl->logpd_dev : nullptr;
-    a.fused = 1; a.n_total = pl->n_total; a.n_begin = pl->n_begin;
+    a.fused = 1; a.n_total = pl->n_total; a.n_begin = pl->n_begin; a.prng_part = g_prng_part;
     a.sp = pl->params_dev; a.ctl = pl->ctl_dev; a.Ybars = pl->Ybars_dev;
     mbd::k_car2d<<<(pl->n_local + 63) / 64, 64, 0, st>>>(a);
     CK(cudaGetLastError());

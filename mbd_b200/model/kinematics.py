@@ -9,6 +9,8 @@ State row: x_i.pos(3) x_i.rot(4, wxyz) xd_i.ang(3) xd_i.vel(3).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .mjcf import System, quat_mul, rotate
@@ -32,7 +34,10 @@ def forward(sys: System, q: np.ndarray, qd: np.ndarray):
         if sys.link_types[l] == "f":
             xpos[l] = q[qs:qs + 3]
             r = q[qs + 3:qs + 7]
-            xrot[l] = r / np.linalg.norm(r)  # MuJoCo semantics: free-joint quaternions are unit
+            # MuJoCo semantics: free-joint quaternions are unit.  Brax's positional kinematics.forward uses q[3:7] as it comes
+            # [brax-recalled]: after the +-0.01 reset noise that is a ~1e-2 relative difference in the reset pose.
+            # MBD_FREE_QUAT_NORMALIZE=0 selects the un-normalised reading (compatibility switch; unpinned either way).
+            xrot[l] = r / np.linalg.norm(r) if os.environ.get("MBD_FREE_QUAT_NORMALIZE", "1") != "0" else r
             xvel[l] = qd[ds:ds + 3]
             xang[l] = qd[ds + 3:ds + 6]
             continue

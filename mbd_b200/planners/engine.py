@@ -27,9 +27,24 @@ from .. import _lib, ops, prng
 from .sharding import ShardPlan
 
 
+def linspace_f32(start: float, stop: float, num: int) -> np.ndarray:
+    """`jnp.linspace(start, stop, num)` with x64 disabled (mbd_planner.py:13-14 leaves it off) **[jax-recalled]**: JAX does not
+    compute `start + k * delta`; it blends the endpoints in float32, `start * (1 - k/(num-1)) + stop * (k/(num-1))`, and appends
+    `stop` itself as the last element.  NumPy's float64 formula rounded to float32 differs from this by an ulp in a few entries
+    (VERDICT r1, row a2); `MBD_LINSPACE=numpy` restores it."""
+    import os
+    f = np.float32
+    if os.environ.get("MBD_LINSPACE", "jax") == "numpy" or num < 2:
+        return np.linspace(start, stop, num, dtype=f)
+    div = f(num - 1)
+    step = (np.arange(num - 1, dtype=f) / div).astype(f)
+    out = (f(start) * (f(1.0) - step)).astype(f) + (f(stop) * step).astype(f)
+    return np.concatenate([out.astype(f), np.array([stop], dtype=f)])
+
+
 def make_schedule(beta0: float, betaT: float, Ndiffuse: int):
     """mbd_planner.py:84-87 in float32."""
-    betas = np.linspace(beta0, betaT, Ndiffuse, dtype=np.float32)
+    betas = linspace_f32(beta0, betaT, Ndiffuse)
     alphas = (np.float32(1.0) - betas).astype(np.float32)
     alphas_bar = np.cumprod(alphas, dtype=np.float32)
     sigmas = np.sqrt(np.float32(1.0) - alphas_bar).astype(np.float32)

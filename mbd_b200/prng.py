@@ -34,8 +34,25 @@ def threefry2x32(key, c0, c1):
     return x0, x1
 
 
+_PARTITIONABLE = False
+
+
+def set_layout(partitionable: bool):
+    """Threefry counter layout of this module AND of the in-kernel samplers (process-wide).  False (default): the legacy layout,
+    `jax_threefry_partitionable=False`, pinned by JAX's known-answer vectors.  True: the partitionable layout that JAX >= 0.5 uses
+    by default **[jax-recalled], unpinned**: `random_bits` element i = xor of the two output words of block (hi, lo) = (0, i);
+    `split(key, n)[i]` = the two output words of block (0, i).  Also settable with MBD_THREEFRY_PARTITIONABLE=1."""
+    global _PARTITIONABLE
+    _PARTITIONABLE = bool(partitionable)
+    from . import _lib
+    _lib.check(_lib.lib().mbd_set_prng_layout(1 if partitionable else 0), "mbd_set_prng_layout")
+
+
 def random_bits(key, total: int) -> np.ndarray:
     """jax.random.bits(key, (total,), uint32): counters iota(total) split in halves (odd -> zero pad)."""
+    if _PARTITIONABLE:
+        o0, o1 = threefry2x32(key, np.zeros(total, dtype=np.uint32), np.arange(total, dtype=np.uint32))
+        return (o0 ^ o1).astype(np.uint32)
     half = (total + 1) // 2
     cnt = np.arange(2 * half, dtype=np.uint32)
     if total % 2:
@@ -49,6 +66,9 @@ def PRNGKey(seed: int) -> np.ndarray:
 
 
 def split(key, num: int = 2) -> np.ndarray:
+    if _PARTITIONABLE:
+        o0, o1 = threefry2x32(key, np.zeros(num, dtype=np.uint32), np.arange(num, dtype=np.uint32))
+        return np.stack([o0, o1], axis=1).astype(np.uint32)
     return random_bits(key, 2 * num).reshape(num, 2)
 
 
@@ -78,6 +98,16 @@ def _threefry_int(k0: int, k1: int, c0: int, c1: int):
 def split2(key):
     """split(key, 2) for the planner's `rng, Y0s_rng = split(rng)` chain: returns (new_key, sub_key) as uint32[2] arrays"""
     k0, k1 = int(key[0]), int(key[1])
+    if _PARTITIONABLE:
+        return (np.array(_threefry_int(k0, k1, 0, 0), dtype=np.uint32), np.array(_threefry_int(k0, k1, 0, 1), dtype=np.uint32))
     a0, a1 = _threefry_int(k0, k1, 0, 2)     # counters iota(4) split in halves: blocks (0, 2) and (1, 3)
     b0, b1 = _threefry_int(k0, k1, 1, 3)
     return np.array([a0, b0], dtype=np.uint32), np.array([a1, b1], dtype=np.uint32)
+
+
+import os as _os
+if _os.environ.get("MBD_THREEFRY_PARTITIONABLE", "0") == "1":   # compatibility switch (ADVICE r1): match a JAX >= 0.5 install
+    try:
+        set_layout(True)
+    except Exception:  # noqa: BLE001 - no library yet (first build): the flag is applied by the first explicit set_layout call
+        _PARTITIONABLE = True

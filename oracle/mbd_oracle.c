@@ -690,12 +690,17 @@ ORC_API int orc_car2d_rollout(const float* params, const float* x0, const float*
 /* ================================================================================== */
 /* JAX PRNG                                                                            */
 /* ================================================================================== */
+/* threefry layout of the samplers below: 0 legacy (pinned by JAX's known-answer vectors), 1 partitionable [jax-recalled] */
+static int g_orc_prng_part = 0;
+ORC_API void orc_set_prng_layout(int partitionable) { g_orc_prng_part = partitionable ? 1 : 0; }
+#define ORC_TOTAL(t) (g_orc_prng_part ? 0u : (uint32_t)(t))
+
 ORC_API void orc_threefry2x32(const uint32_t* key, const uint32_t* ctr, uint32_t* out) {
   mbd_threefry2x32(key[0], key[1], ctr[0], ctr[1], &out[0], &out[1]);
 }
 /* jax.random.bits(key, (total,)) */
 ORC_API void orc_random_bits(const uint32_t* key, uint32_t total, uint32_t* out) {
-  for (uint32_t i = 0; i < total; ++i) out[i] = mbd_random_bits_at(key[0], key[1], i, total);
+  for (uint32_t i = 0; i < total; ++i) out[i] = mbd_random_bits_at(key[0], key[1], i, ORC_TOTAL(total));
 }
 /* jax.random.normal(key, shape) flattened; [begin, end) of `total` elements */
 ORC_API void orc_normal(const uint32_t* key, uint32_t total, uint32_t begin, uint32_t end, float* out, int nthreads) {
@@ -704,7 +709,7 @@ ORC_API void orc_normal(const uint32_t* key, uint32_t total, uint32_t begin, uin
 #endif
 #pragma omp parallel for schedule(static)
   for (int64_t i = begin; i < (int64_t)end; ++i)
-    out[i - begin] = mbd_bits_to_normal(mbd_random_bits_at(key[0], key[1], (uint32_t)i, total));
+    out[i - begin] = mbd_bits_to_normal(mbd_random_bits_at(key[0], key[1], (uint32_t)i, ORC_TOTAL(total)));
 }
 /* reverse_once sampling, mbd_planner.py:103-106: clip(eps*sigma + Ybar, -1, 1); Ybar [H*nu] */
 ORC_API void orc_sample_Y0s(const uint32_t* key, int n_total, int n_begin, int n_end, int HNu, float sigma,
@@ -717,7 +722,7 @@ ORC_API void orc_sample_Y0s(const uint32_t* key, int n_total, int n_begin, int n
   for (int i = n_begin; i < n_end; ++i)
     for (int e = 0; e < HNu; ++e) {
       uint32_t idx = (uint32_t)i * (uint32_t)HNu + (uint32_t)e;
-      float eps = mbd_bits_to_normal(mbd_random_bits_at(key[0], key[1], idx, total));
+      float eps = mbd_bits_to_normal(mbd_random_bits_at(key[0], key[1], idx, ORC_TOTAL(total)));
       float y = eps * sigma + Ybar[e];
       out[(size_t)(i - n_begin) * HNu + e] = clampf(y, -1.0f, 1.0f);
     }

@@ -145,8 +145,21 @@ def prng_key(seed: int):
     return np.array([0, seed & 0xFFFFFFFF], dtype=np.uint32)
 
 
+_PART = False
+
+
+def set_prng_layout(partitionable: bool):
+    """legacy (default, pinned by JAX's KATs) or partitionable [jax-recalled] threefry layout for every sampler of the oracle"""
+    global _PART
+    _PART = bool(partitionable)
+    lib().orc_set_prng_layout(1 if partitionable else 0)
+
+
 def split(key, num=2):
-    """jax.random.split: threefry_2x32(key, iota(2*num)).reshape(num, 2)."""
+    """jax.random.split: legacy threefry_2x32(key, iota(2*num)).reshape(num, 2); partitionable: key i = block(key, (0, i))."""
+    if _PART:
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        return np.stack([threefry2x32(key, np.uint32([0, i])) for i in range(num)])
     return random_bits(key, 2 * num).reshape(num, 2)
 
 

@@ -18,7 +18,14 @@ f32 = np.float32
 
 def make_schedule(beta0, betaT, Ndiffuse):
     """mbd_planner.py:84-87."""
-    betas = np.linspace(beta0, betaT, Ndiffuse, dtype=f32)
+    # jnp.linspace in float32 [jax-recalled]: start*(1 - k/(N-1)) + stop*(k/(N-1)), endpoint appended (see mbd_b200/planners/engine.py)
+    import os
+    if os.environ.get("MBD_LINSPACE", "jax") == "numpy" or Ndiffuse < 2:
+        betas = np.linspace(beta0, betaT, Ndiffuse, dtype=f32)
+    else:
+        step = (np.arange(Ndiffuse - 1, dtype=f32) / f32(Ndiffuse - 1)).astype(f32)
+        betas = np.concatenate([((f32(beta0) * (f32(1.0) - step)).astype(f32) + (f32(betaT) * step).astype(f32)).astype(f32),
+                                np.array([betaT], dtype=f32)])
     alphas = (f32(1.0) - betas).astype(f32)
     alphas_bar = np.cumprod(alphas, dtype=f32)
     sigmas = np.sqrt(f32(1.0) - alphas_bar).astype(f32)

@@ -51,3 +51,27 @@ def test_normal_slices_are_consistent(orc):
     assert np.abs(allY).max() <= 1.0
     z = orc.normal(np.uint32([1, 2]), (200000,))
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+
+
+def test_partitionable_layout_is_self_consistent():
+    """the compatibility switch for JAX >= 0.5 (jax_threefry_partitionable=True) [jax-recalled, unpinned]: host key management,
+    the oracle's samplers and (on the GPU, tests/test_rollout_gpu.py) the in-kernel sampler implement the SAME layout:
+    bits[i] = o0 ^ o1 of block (0, i); split(key, n)[i] = (o0, o1) of block (0, i)"""
+    from mbd_b200 import prng
+    from oracle import oracle as orc
+    key = prng.PRNGKey(42)
+    try:
+        prng._PARTITIONABLE = True          # host layout only (no GPU library call in a CPU test)
+        orc.set_prng_layout(True)
+        b = prng.random_bits(key, 7)
+        o0, o1 = prng.threefry2x32(key, np.zeros(7, np.uint32), np.arange(7, dtype=np.uint32))
+        assert np.array_equal(b, o0 ^ o1) and np.array_equal(b, orc.random_bits(key, 7))
+        assert np.array_equal(prng.split(key, 3), orc.split(key, 3))
+        a, c = prng.split2(key)
+        assert np.array_equal(np.stack([a, c]), prng.split(key, 2))
+        assert np.array_equal(np.clip(orc.normal(key, (5,)), -1, 1).view(np.uint32),
+                              orc.sample_Y0s(key, 1, 5, 1.0, np.zeros(5, np.float32)).ravel().view(np.uint32))
+    finally:
+        prng._PARTITIONABLE = False
+        orc.set_prng_layout(False)
+    assert not np.array_equal(prng.random_bits(key, 7), b)     # and it differs from the legacy layout

@@ -245,3 +245,26 @@ def test_argument_errors(hr):
         ops.rollout(m, torch.as_tensor(st), torch.zeros((4, 5, 17)))         # CPU tensors: no fallback
     with pytest.raises(MbdError):
         ops.sample(np.uint32([1, 2]), 10, 8, 5, 4, 1.0, torch.zeros(4, device=DEV))  # slice past the end
+
+
+def test_partitionable_threefry_layout_on_the_gpu(orc, hr):
+    """compatibility switch for JAX >= 0.5 (mbd_set_prng_layout): the in-kernel sampler and the oracle's implement the same
+    [jax-recalled] partitionable layout — fused sampling + rollouts agree bit for bit, and differ from the legacy stream"""
+    from mbd_b200 import prng
+    env, blob, st, m = hr
+    key = np.uint32([12, 34]); n, H = 96, 6
+    Yb = torch.zeros(H * 17, device=DEV)
+    sti = torch.as_tensor(st, device=DEV)
+    Y = torch.empty((n, H * 17), device=DEV); r = torch.empty(n, device=DEV)
+    ops.sample_rollout(m, sti, key, n, 0, n, H, 0.7, Yb, Y, r)
+    legacy = Y.cpu().numpy().copy()
+    try:
+        prng.set_layout(True); orc.set_prng_layout(True)
+        ops.sample_rollout(m, sti, key, n, 0, n, H, 0.7, Yb, Y, r)
+        ref = orc.sample_Y0s(key, n, H * 17, 0.7, np.zeros(H * 17, np.float32))
+        assert_bit_exact(Y.cpu().numpy(), ref, "partitionable Y0s")
+        out = orc.xpbd_rollout(blob, st, ref.reshape(n, H, 17))
+        assert_bit_exact(r.cpu().numpy(), out["rews"], "returns")
+    finally:
+        prng.set_layout(False); orc.set_prng_layout(False)
+    assert not np.array_equal(legacy, Y.cpu().numpy())
