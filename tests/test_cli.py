@@ -1,5 +1,6 @@
 """Args / recommended-parameter override logic (mbd_planner.py:18-35,45-69) and the env registry."""
 import dataclasses
+import os
 
 import pytest
 
@@ -65,3 +66,35 @@ def test_reset_is_the_reference_chain():
     assert st.obs.shape == (47,) and st.reward == 0 and st.done == 0
     st2 = mbd_b200.envs.get_env("humanoidtrack").reset(None)
     assert np.allclose(st2.pipeline_state.q[7:24], 0, atol=1e-7) and np.allclose(st2.pipeline_state.qd, 0)
+
+
+def test_schedule_upload_helpers():
+    """host pieces of the graph-captured solve: the Y0s_rng chain of a whole solve equals the per-step `rng, Y0s_rng = split(rng)`
+    of mbd_planner.py:103; the float32 linspace keeps the endpoints exactly and the schedule KATs of SURVEY 8(d)"""
+    import numpy as np
+    from mbd_b200 import prng
+    from mbd_b200.planners import engine as eng
+    rng_exp = prng.split(prng.split(prng.PRNGKey(0))[0])[0]
+    keys = eng.key_chain(rng_exp, 12)
+    r = rng_exp
+    for i in range(11, 0, -1):
+        r, k = prng.split(r)
+        assert np.array_equal(keys[i], k)
+    assert not keys[0].any()
+    for N, sig in ((100, 0.6305), (200, 0.7981), (300, 0.8839)):
+        betas, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, N)
+        assert betas.dtype == np.float32 and betas[0] == np.float32(1e-4) and betas[-1] == np.float32(1e-2) and abs(float(sigmas[-1]) - sig) < 5e-5
+    c = eng.update_coef(alphas, alphas_bar, 5)
+    assert all(np.asarray(v).dtype == np.float32 for v in c) and len(c) == 5
+
+
+def test_brax_asset_lookup_order(tmp_path, monkeypatch):
+    """envs/base.py::brax_asset: $MBD_BRAX_ASSETS first (a user's own Brax files), then the repo's restated models"""
+    from mbd_b200.envs.base import ASSET_DIR, brax_asset
+    monkeypatch.delenv("MBD_BRAX_ASSETS", raising=False)
+    assert os.path.samefile(brax_asset("hopper.xml"), os.path.join(ASSET_DIR, "hopper.xml"))
+    (tmp_path / "hopper.xml").write_text(open(os.path.join(ASSET_DIR, "hopper.xml")).read())
+    monkeypatch.setenv("MBD_BRAX_ASSETS", str(tmp_path))
+    assert os.path.samefile(brax_asset("hopper.xml"), tmp_path / "hopper.xml")
+    with pytest.raises(FileNotFoundError):
+        brax_asset("nope.xml")
