@@ -98,3 +98,24 @@ def test_brax_asset_lookup_order(tmp_path, monkeypatch):
     assert os.path.samefile(brax_asset("hopper.xml"), tmp_path / "hopper.xml")
     with pytest.raises(FileNotFoundError):
         brax_asset("nope.xml")
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` (the driver's CPU arm, no GPU needed): one JSON line with the contract's keys, the same
+    `config.workload` string as the GPU arm, threads taken from the cgroup / affinity (not from torchrun's OMP_NUM_THREADS=1)"""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3", "--cpu-samples", "128"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["config"]["workload"] == "humanoidrun Nsample=8192 Hsample=50 n_frames=7 Ndiffuse=300"
+    assert line["cpu_baseline"]["cores"] >= 1 and line["e2e"]["h2d_bytes_per_step"] == 0
+    # other ranks of a torchrun launch exit silently
+    r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1"], capture_output=True, text=True,
+                        timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
