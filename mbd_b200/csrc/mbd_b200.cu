@@ -1021,7 +1021,6 @@ struct mbd_model {
   int nwarps2;
   signed char gw2[32];  // two-group CTA: warp -> (group << 4) | slot
   int nlate;            // jointed leaf links with contacts (SyncGroup's late leaves)
-  bool named_ok;        // the tree fits the named edge barriers (2 ids per parent node <= 15) and no reward reads another link's row
   mbd::RolloutArgs::LinkCfgP cfg[MBD_MAXL];   // warp-uniform topology handed to the kernels through the parameter bank
 };
 
@@ -1224,12 +1223,6 @@ mbd_model* mbd_model_create(const uint32_t* blob_host, size_t nwords) {
   if (m->L < 1 || m->L > MBD_MAXL || m->ntrack > MBD_MAXTRACK) { delete m; snprintf(g_err, sizeof(g_err), "bad link count"); return nullptr; }
   build_pairing(m, blob_host);
   if (cudaGetDevice(&m->device) != cudaSuccess) m->device = 0;
-  {
-    int nparents = 0;
-    for (int l = 0; l < m->L; ++l) nparents += hi[MBD_HDR_WORDS + MBD_F_CHILD0 * MBD_MAXL + l] >= 0 ? 1 : 0;
-    // cartpole's reward on link 0 reads link 1's published rotation after the end-of-substep barrier: needs the CTA-wide policy
-    m->named_ok = 2 * nparents <= 15 && hi[MBD_H_REWARD] != MBD_REWARD_CARTPOLE;
-  }
   m->max_ncon = 0;
   for (int l = 0; l < m->L; ++l) { int nc = hi[MBD_HDR_WORDS + MBD_F_NCON * MBD_MAXL + l]; if (nc > m->max_ncon) m->max_ncon = nc; }
   if (m->max_ncon > MBD_MAXCON) { delete m; snprintf(g_err, sizeof(g_err), "too many contacts on one link"); return nullptr; }
@@ -1298,8 +1291,7 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   //   n <= 148 * 32  one 32-sample CTA per SM, warp per link, named edge barriers, uncapped registers           -> v3
   //   larger         64 samples per SM, two per lane on the packed FFMA2 / FMUL2 / FADD2 path (half the issue slots per
   //                  sample; with the topology in uniform registers it beats the two-group scalar CTA by 8 %)      -> v9
-  if (variant == 0) variant = (L == 11) ? (a.n <= 148 * 8 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 9 : 2)))   // contact-heavy models (humanoidstandup): CTA barriers
-                                        : ((m->named_ok && a.n <= 148 * 32) ? 3 : 2);   // other models: edge barriers while one CTA per SM suffices
+  if (variant == 0) variant = (L == 11) ? (a.n <= 148 * 8 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 9 : 2))) : 2;   // contact-heavy models (humanoidstandup): CTA barriers
   if ((variant == 8 || variant == 9) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
   if (variant == 8 || variant == 9) {
     // packed kernel: 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
@@ -1354,7 +1346,6 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
       } else if (L == 11 && variant == 2) MBD_LAUNCH_WPL(11, 2, 0, 1, grid, 32 * L);       // CTA-wide barriers
       else if (L == 11 && variant == 3 && grid <= 148) MBD_LAUNCH_WPL(11, 1, 2, 1, grid, 32 * L);  // one CTA per SM: no register cap
       else if (L == 11 && variant == 3) MBD_LAUNCH_WPL(11, 2, 2, 1, grid, 32 * L);  // named edge barriers
-      else if (variant == 3 && m->named_ok) MBD_LAUNCH_WPL(MBD_MAXL, 1, 2, 1, grid, 32 * L);   // any tree with <= 7 parent nodes: named edge barriers
       else MBD_LAUNCH_WPL(MBD_MAXL, 1, 0, 1, grid, 32 * L);
     }
   } else {

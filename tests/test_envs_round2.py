@@ -145,7 +145,7 @@ def test_cartpole_energy_sanity():
 # GPU: kernels vs oracle, bit for bit
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("name", NEW_ENVS)
 def test_rollout_kernels_match_oracle_bit_exact(name, variant):
     import torch
