@@ -63,6 +63,13 @@
 #ifndef ORC_CONTACT_MIDPOINT       /* 1: contact position c - n (r + dist/2) (MJX plane_sphere); 0: the sphere's surface point c - n r */
 #define ORC_CONTACT_MIDPOINT 1
 #endif
+#ifndef ORC_TANGENT_EPS_FORM       /* tangent direction of the friction terms: 0: exact normalise with a zero guard (math.normalize);
+                                      1: dx / (1e-6 + |dx|), the form Brax v1's colliders use [brax-recalled] */
+#define ORC_TANGENT_EPS_FORM 0
+#endif
+#ifndef ORC_EPS_TANGENT            /* 1: the tangential XPBD denominators carry the same regulariser as the normal ones; 0: they do not */
+#define ORC_EPS_TANGENT 1
+#endif
 #ifndef ORC_EULER_ACOS             /* 0: joint angles from matrix entries with atan2 only; 1: the middle angle as acos(clip(cos)) * sign(sin),
                                       the line-of-nodes form (libm acosf: oracle-only, never bit-compared) */
 #define ORC_EULER_ACOS 0
@@ -226,11 +233,11 @@ static inline void contact_position_plane(const Model* m, int l, int ci, float i
   v3 pbar = vadd(p_prev, vrotate(rl, q_prev));
   float dx = cp.x - pbar.x, dy = cp.y - pbar.y;
   float ct = sqrtf(fmaf(dy, dy, dx * dx));
-  float inv = (ct == 0.0f) ? 0.0f : 1.0f / ct;
+  float inv = ORC_TANGENT_EPS_FORM ? 1.0f / (1e-6f + ct) : ((ct == 0.0f) ? 0.0f : 1.0f / ct);
   float ntx = dx * inv, nty = dy * inv;
   float c1 = -(r.z * nty), c2 = r.z * ntx, c3 = fmaf(r.x, nty, -(r.y * ntx));
   float wt = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
-  float dlt = -ct / (wt + ORC_EPS);
+  float dlt = -ct / (wt + (ORC_EPS_TANGENT ? ORC_EPS : 0.0f));
   int stat = coll && (fabsf(dlt) < (ORC_STATIC_FRICTION_MU ? mu : 1.0f) * fabsf(dl));
   float mm = stat ? dlt : 0.0f;
   float ptx = ntx * mm, pty = nty * mm;
@@ -247,13 +254,13 @@ static inline void contact_velocity_plane(const Model* m, int l, int ci, float i
   v3 rel = vadd(v, vcross(w, r));
   float vn = rel.z;
   float vtn = sqrtf(fmaf(rel.y, rel.y, rel.x * rel.x));
-  float inv = (vtn == 0.0f) ? 0.0f : 1.0f / vtn;
+  float inv = ORC_TANGENT_EPS_FORM ? 1.0f / (1e-6f + vtn) : ((vtn == 0.0f) ? 0.0f : 1.0f / vtn);
   float tdx = rel.x * inv, tdy = rel.y * inv;
   float fr = mu * fabsf(dl) * m->inv_dt;                                /* dynamic friction bound mu |dlambda| / dt */
   float mag = fr < vtn ? fr : vtn;
   float c1 = -(r.z * tdy), c2 = r.z * tdx, c3 = fmaf(r.x, tdy, -(r.y * tdx));
   float wd = im + fmaf(c3, c3, fmaf(c2, c2, c1 * c1));
-  float kd = 1.0f / (wd + ORC_EPS);
+  float kd = 1.0f / (wd + (ORC_EPS_TANGENT ? ORC_EPS : 0.0f));
   float pdx = (tdx * -mag) * kd, pdy = (tdy * -mag) * kd;
   v3 rel_old = vadd(v_before, vcross(w_before, r));
   float vn_old = rel_old.z;

@@ -45,6 +45,8 @@ SWITCHES = {  # name -> candidate values (first = the default the CUDA kernels i
     "ORC_STATIC_FRICTION_MU": [1, 0],
     "ORC_SINKING_GATE": [1, 0],
     "ORC_CONTACT_MIDPOINT": [1, 0],
+    "ORC_TANGENT_EPS_FORM": [0, 1],
+    "ORC_EPS_TANGENT": [1, 0],
     "ORC_EULER_ACOS": [0, 1],
     "ORC_EPS": ["1e-6f", "0.0f"],
 }
@@ -176,7 +178,7 @@ def self_test():
         np.savez(path, states=np.float32(states), action=action)
         SW = dict(SWITCHES)
         for k in list(SWITCHES):
-            if k not in ("ORC_SINKING_GATE", "ORC_CONTACT_MIDPOINT", "ORC_STATIC_FRICTION_MU"):
+            if k not in ("ORC_SINKING_GATE", "ORC_CONTACT_MIDPOINT", "ORC_TANGENT_EPS_FORM"):
                 SWITCHES[k] = SWITCHES[k][:1]          # keep the grid small: 8 builds
         try:
             rows = compare(path)
