@@ -60,7 +60,8 @@ def apply_recommended_params(args: Args) -> Args:
         args.Ndiffuse = NDIFFUSE_RECOMMEND.get(args.env_name, args.Ndiffuse)
         args.Nsample = NSAMPLE_RECOMMEND.get(args.env_name, args.Nsample)
         args.Hsample = HSAMPLE_RECOMMEND.get(args.env_name, args.Hsample)
-        print(f"override temp_sample to {args.temp_sample}")
+        if _is_main():   # one line per job, as in the single-process reference (every rank of a torchrun job runs this)
+            print(f"override temp_sample to {args.temp_sample}")
     return args
 
 
