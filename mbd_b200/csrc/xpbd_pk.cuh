@@ -210,7 +210,7 @@ PK_FN void contact_velocity_plane(const Model<T>& M, int l, int ci, T im, T inv_
   const T zero = bc<T>(0.0f);
   const T mu = M.l(MBD_F_CON0 + ci * MBD_CON_STRIDE + 4, l);
   V<T> r = vsub(cp, p);
-  V<T> rel = vadd_nf(v, vcross(w, r));   // v is a product (project_xd)
+  V<T> rel = vadd(v, vcross(w, r));   // v is a product (project_xd)
   T vn = rel.z;
   T vtn = sqrt_(fma(rel.y, rel.y, mul(rel.x, rel.x)));
   T inv = sel(eq(vtn, zero), zero, rcp_(vtn));
@@ -226,7 +226,7 @@ PK_FN void contact_velocity_plane(const Model<T>& M, int l, int ci, T im, T inv_
   T rest = mul(neg(elasticity), vn_old);
   rest = sel(lt(rest, zero), rest, zero);
   T wn = add(im, fma(r.x, r.x, mul(r.y, r.y)));
-  T prz = mul(add_nf(neg(vn), rest), rcp_(add(wn, bc<T>(1e-6f))));   // rest may be a product
+  T prz = mul(add(neg(vn), rest), rcp_(add(wn, bc<T>(1e-6f))));   // rest may be a product
   auto live = eq(dl, zero);   // dl == 0: no impulse at all
   V<T> P = mkV(sel(live, zero, pdx), sel(live, zero, pdy), sel(live, zero, sel(le(vn_old, zero), prz, zero)));
   dv = vadd_nf(dv, vscale(P, im));
@@ -247,7 +247,7 @@ PK_FN void phase_A(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
     Q<T> a_p = qmul(qp, M.l4(MBD_F_PQ, c.l));
     Q<T> a_c = qmul(s.q, M.l4(MBD_F_JQ, c.l));
     Q<T> j = qmul(qconj(a_p), a_c);
-    V<T> jd = vinv_rotate(vsub_nf(s.w, wp), a_p);   // s.w is a product after project_xd
+    V<T> jd = vinv_rotate(vsub(s.w, wp), a_p);   // s.w is a product after project_xd
     V<T> tq = vscale(jd, neg(M.l(MBD_F_ANG_DAMP, c.l)));
     if (c.ndof == 1) {
       T psi, r10, r20;
@@ -287,7 +287,7 @@ PK_FN void phase_B(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
   const T dt = M.h(MBD_H_DT), ad = M.h(MBD_H_ANG_DAMP), vd = M.h(MBD_H_VEL_DAMP);
   s.w = mkV(fma(acc.x, dt, mul(s.w.x, ad)), fma(acc.y, dt, mul(s.w.y, ad)), fma(acc.z, dt, mul(s.w.z, ad)));
   s.v = mkV(fma(M.h(MBD_H_GX), dt, mul(s.v.x, vd)), fma(M.h(MBD_H_GY), dt, mul(s.v.y, vd)), fma(M.h(MBD_H_GZ), dt, mul(s.v.z, vd)));
-  s.q = qnormalize(qadd_nf(s.q, vqmul(vscale(s.w, M.h(MBD_H_HALF_DT)), s.q)));   // s.q is a product (qnormalize)
+  s.q = qnormalize(qadd(s.q, vqmul(vscale(s.w, M.h(MBD_H_HALF_DT)), s.q)));   // s.q is a product (qnormalize)
   s.p = vfma(s.v, dt, s.p);
   S.put_p(c.l, s.p);
   S.put_q(c.l, s.q);
@@ -335,7 +335,7 @@ PK_FN void phase_C(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
       axis_angle_ang(j, M.l(MBD_F_PARITY, c.l), ja);
       T e0 = sub(ja.ang[0], clamp_(ja.ang[0], M.l(b0 + MBD_D_LO, c.l), M.l(b0 + MBD_D_HI, c.l)));
       T e1 = sub(ja.ang[1], clamp_(ja.ang[1], M.l(b1 + MBD_D_LO, c.l), M.l(b1 + MBD_D_HI, c.l)));
-      T e2 = sub_nf(ja.ang[2], clamp_(ja.ang[2], M.l(b2 + MBD_D_LO, c.l), M.l(b2 + MBD_D_HI, c.l)));
+      T e2 = sub(ja.ang[2], clamp_(ja.ang[2], M.l(b2 + MBD_D_LO, c.l), M.l(b2 + MBD_D_HI, c.l)));
       dqj = vscale(ja.ax[0], e0);
       dqj = vfma(ja.ax[1], e1, dqj);
       dqj = vfma(ja.ax[2], e2, dqj);
@@ -369,10 +369,10 @@ PK_FN void phase_D(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
 #pragma unroll
 #endif
     for (int i = 0; i < MBD_MAXCHILD; ++i) {
-      if (c.child[i] >= 0) { dp = vadd_nf(dp, S.e3(c.child[i], 0)); dq = qadd(dq, S.e4(c.child[i], 3)); }   // dp starts as a product
+      if (c.child[i] >= 0) { dp = vadd(dp, S.e3(c.child[i], 0)); dq = qadd(dq, S.e4(c.child[i], 3)); }   // dp starts as a product
     }
-    s.p = vadd_nf(s.p, dp);
-    s.q = qnormalize(qadd_nf(s.q, dq));
+    s.p = vadd(s.p, dp);
+    s.q = qnormalize(qadd(s.q, dq));
   }
   T dlam[CMAX];
   V<T> cpos[CMAX];
@@ -409,8 +409,8 @@ PK_FN void phase_D(const Model<T>& M, const Cfg& c, const Smem<T>& S, State<T>& 
       if (ci < c.ncon)
         contact_velocity_plane(M, c.l, ci, M.l(MBD_F_INV_MASS, c.l), M.h(MBD_H_INV_DT), M.h(MBD_H_ELASTICITY), s.p, v0, w0, k.v_before,
                                k.w_before, cpos[ci], dlam[ci], dv, dw);
-    s.v = vadd_nf(s.v, dv);   // s.v, s.w are products (project_xd)
-    s.w = vadd_nf(s.w, dw);
+    s.v = vadd(s.v, dv);   // s.v, s.w are products (project_xd)
+    s.w = vadd(s.w, dw);
   }
   S.put_q(c.l, s.q);
   S.put_w(c.l, s.w);

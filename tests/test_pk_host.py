@@ -127,3 +127,15 @@ def test_simd_cpu_arm_matches_the_scalar_oracle():
         assert np.array_equal(out["final"].view(np.uint32), ref["final"].view(np.uint32))
     hop = mbd_b200.envs.get_env("hopper")   # slide dofs / other rewards are not covered: the caller falls back to the scalar oracle
     assert orc.simd_rollout(hop.blob, hop.pipeline_init(hop.sys.init_q, np.zeros(6)).raw, np.zeros((4, 2, 3), np.float32)) is None
+
+
+def test_no_packed_contraction_in_the_product_kernels():
+    """the same check on the product kernels themselves (scripts/check_pk_contraction.py compiles csrc/mbd_b200.cu to PTX and SASS):
+    no packed multiply of any k_rollout_pk instantiation disappears into an FFMA2.  Round 2 turned 10 of the 21 `*_nf` sums back into
+    packed adds after a per-site search showed that ptxas does not contract there (their product operands have other uses)."""
+    import shutil, sys
+    if not shutil.which("nvcc"):
+        pytest.skip("CUDA toolkit not available")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "check_pk_contraction.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.stdout.count(" ok") >= 8
