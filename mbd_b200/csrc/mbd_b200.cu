@@ -1536,16 +1536,24 @@ static int step_tail_launch(const mbd_step_plan* pl, cudaStream_t st, cudaEvent_
 
 // ---- one diffusion step with device-resident parameters: three launches, CUDA-graph capturable --------------------------
 static int step_launch_impl(const mbd_step_plan* pl, cudaStream_t st, cudaEvent_t ev_mid, cudaEvent_t ev_mid2 = nullptr) {
-  if (!pl || !pl->state_init_dev || !pl->params_dev || !pl->ctl_dev || !pl->Ybars_dev || !pl->Y0s_dev || !pl->rews_dev ||
-      !pl->rews_all_dev || !pl->logp_dev || !pl->weights_dev || !pl->runs_dev || !pl->partial_dev || !pl->scalars_dev)
-    return MBD_EINVAL;
-  if (pl->n_local <= 0 || pl->H <= 0 || pl->nu <= 0 || pl->n_begin < 0 || pl->n_begin + pl->n_local > pl->n_total) return MBD_EINVAL;
-  if (pl->P < 1 || pl->P > 8 || pl->rank < 0 || pl->rank >= pl->P || (pl->P > 1 && !pl->peer_base_ptrs)) return MBD_EINVAL;
+#define STEP_REQUIRE(cond, msg)                                             \
+  do {                                                                      \
+    if (!(cond)) { snprintf(g_err, sizeof(g_err), "mbd_step_launch: %s", msg); return MBD_EINVAL; } \
+  } while (0)
+  STEP_REQUIRE(pl != nullptr, "plan is NULL");
+  STEP_REQUIRE(pl->state_init_dev && pl->params_dev && pl->ctl_dev && pl->Ybars_dev, "state_init / params / ctl / Ybars must be set");
+  STEP_REQUIRE(pl->Y0s_dev && pl->rews_dev && pl->rews_all_dev && pl->logp_dev && pl->weights_dev && pl->runs_dev && pl->partial_dev &&
+               pl->scalars_dev, "a work buffer is NULL");
+  STEP_REQUIRE(pl->n_local > 0 && pl->H > 0 && pl->nu > 0 && pl->n_begin >= 0 && pl->n_begin + pl->n_local <= pl->n_total,
+               "bad sample range (n_begin + n_local must lie inside n_total)");
+  STEP_REQUIRE(pl->P >= 1 && pl->P <= 8 && pl->rank >= 0 && pl->rank < pl->P, "rank count must be 1..8");
+  STEP_REQUIRE(pl->P == 1 || pl->peer_base_ptrs != nullptr, "sharded step needs the peers' symmetric-buffer addresses");
   const int HNu = pl->H * pl->nu;
-  if ((HNu + mbd::kUpdThreads - 1) / mbd::kUpdThreads > MBD_STEP_MAX_COLBLOCKS) return MBD_EINVAL;
-  if ((uint64_t)pl->n_total * (uint64_t)HNu >= 0xffffffffull) return MBD_EINVAL;
+  STEP_REQUIRE((HNu + mbd::kUpdThreads - 1) / mbd::kUpdThreads <= MBD_STEP_MAX_COLBLOCKS, "H * Nu exceeds 27 * 256 columns");
+  STEP_REQUIRE((uint64_t)pl->n_total * (uint64_t)HNu < 0xffffffffull, "Nsample * H * Nu must stay below 2^32 (threefry counter layout)");
   const bool demo = pl->xref_dev != nullptr;
-  if (demo && (pl->href <= 0 || !pl->logpd_dev || !pl->logpd_all_dev)) return MBD_EINVAL;
+  STEP_REQUIRE(!demo || (pl->href > 0 && pl->logpd_dev && pl->logpd_all_dev), "demo step needs href, logpd and logpd_all");
+#undef STEP_REQUIRE
   // 1. sampling + rollouts
   if (pl->model) {
     if (pl->model->nu != pl->nu) return MBD_EINVAL;
