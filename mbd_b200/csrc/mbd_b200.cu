@@ -1021,6 +1021,8 @@ struct mbd_model {
   int nwarps2;
   signed char gw2[32];  // two-group CTA: warp -> (group << 4) | slot
   int nlate;            // jointed leaf links with contacts (SyncGroup's late leaves)
+  bool named_ok;        // SyncNamed needs two hardware barrier ids (1..15) per link that has children: at most 7 such links
+  bool pk_ok;           // the packed kernel (xpbd_pk.cuh) covers this model: 11 links, hinge dofs only, a reward it implements
   mbd::RolloutArgs::LinkCfgP cfg[MBD_MAXL];   // warp-uniform topology handed to the kernels through the parameter bank
 };
 
@@ -1043,7 +1045,8 @@ static void build_pairing(mbd_model* m, const uint32_t* blob) {
     m->cfg[l].smask = (signed char)((live && li(MBD_F_NDOF, l) > 0) ? li(MBD_F_SLIDE, l) : 0);
     for (int k = 0; k < MBD_MAXCHILD; ++k) m->cfg[l].child[k] = (signed char)(live ? li(MBD_F_CHILD0 + k, l) : -1);
   }
-  for (int l = 0; l < L; ++l) m->nlate += (li(MBD_F_CHILD0, l) < 0 && li(MBD_F_NCON, l) > 0 && li(MBD_F_NDOF, l) > 0) ? 1 : 0;
+  // must be the predicate SyncGroup::end_D uses (leaf && contacts; a single-link free body with contacts counts too)
+  for (int l = 0; l < L; ++l) m->nlate += (li(MBD_F_CHILD0, l) < 0 && li(MBD_F_NCON, l) > 0) ? 1 : 0;
   // two-group CTA: warp w -> (group, slot).  Both groups sit on ALL FOUR SM sub-partition schedulers (group = bit 0 xor bit 2
   // of the warp id) and group 1 starts ~half a substep late (g_group_stagger): the two groups then demand the fp32 pipe in
   // different phases.  Measured on humanoidrun 8192 x 50 (scripts/gpu_stagger_sweep.py, profiles/r02_experiments.md):
@@ -1226,6 +1229,17 @@ mbd_model* mbd_model_create(const uint32_t* blob_host, size_t nwords) {
   m->max_ncon = 0;
   for (int l = 0; l < m->L; ++l) { int nc = hi[MBD_HDR_WORDS + MBD_F_NCON * MBD_MAXL + l]; if (nc > m->max_ncon) m->max_ncon = nc; }
   if (m->max_ncon > MBD_MAXCON) { delete m; snprintf(g_err, sizeof(g_err), "too many contacts on one link"); return nullptr; }
+  {
+    // the packed (two samples per lane) physics has no slide-dof path and evaluates only the rewards of the free-root envs
+    const int rk = hi[MBD_H_REWARD];
+    bool slides = false;
+    for (int l = 0; l < m->L; ++l) slides = slides || m->cfg[l].smask != 0;
+    int nparents = 0;
+    for (int l = 0; l < m->L; ++l) nparents += m->cfg[l].child[0] >= 0 ? 1 : 0;
+    m->named_ok = 2 * nparents <= 15;
+    m->pk_ok = m->L == mbd::kPkLinks && !slides &&
+               (rk == MBD_REWARD_HUMANOIDRUN || rk == MBD_REWARD_HUMANOIDTRACK || rk == MBD_REWARD_HUMANOIDSTANDUP || rk == MBD_REWARD_ANT);
+  }
   if (cudaMalloc(&m->blob_dev, nwords * 4) != cudaSuccess || cudaMemcpy(m->blob_dev, blob_host, nwords * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "mbd_model_create: cudaMalloc/cudaMemcpy failed");
     delete m;
@@ -1291,8 +1305,9 @@ static int launch_rollout(bool fused, mbd::RolloutArgs a, const mbd_model* m, cu
   //   n <= 148 * 32  one 32-sample CTA per SM, warp per link, named edge barriers, uncapped registers           -> v3
   //   larger         64 samples per SM, two per lane on the packed FFMA2 / FMUL2 / FADD2 path (half the issue slots per
   //                  sample; with the topology in uniform registers it beats the two-group scalar CTA by 8 %)      -> v9
-  if (variant == 0) variant = (L == 11) ? (a.n <= 148 * 8 ? 1 : (a.n <= 148 * 32 ? 3 : (m->max_ncon <= 2 ? 9 : 2))) : 2;   // contact-heavy models (humanoidstandup): CTA barriers
-  if ((variant == 8 || variant == 9) && L != mbd::kPkLinks) variant = 2;   // the packed kernel is built for 11-link models
+  if (variant == 0) variant = (L == 11) ? (a.n <= 148 * 8 ? 1 : (a.n <= 148 * 32 ? 3 : ((m->max_ncon <= 2 && m->pk_ok) ? 9 : 2))) : 2;   // contact-heavy models (humanoidstandup): CTA barriers
+  if (!m->named_ok) variant = variant == 3 ? 2 : (variant == 9 ? 8 : variant);   // deep trees: not enough named barriers
+  if ((variant == 8 || variant == 9) && !m->pk_ok) variant = 2;   // the packed kernel is built for 11-link hinge-only models (no slide dofs)
   if (variant == 8 || variant == 9) {
     // packed kernel: 64 samples per CTA, two per lane (variant 8: group barriers with decoupled leaves, 9: named edge barriers)
     memcpy(a.wl, m->wl1, sizeof(a.wl));
