@@ -150,8 +150,10 @@ struct SyncGroup {
 struct SyncNamed {
   int my_pose_id, my_terms_id, my_count;       // valid when this link has children (else 0)
   int par_pose_id, par_terms_id, par_count;    // ids owned by the parent (0 when parent is the world / none)
+  // No fence before the arrival: bar.arrive / bar.sync order the arriving thread's earlier shared-memory accesses before the
+  // barrier completes for every participant (the PTX ISA's own producer / consumer example is st.shared; bar.arrive on one side,
+  // bar.sync; ld.shared on the other).  Round 1 had a __threadfence_block() here = four MEMBAR.SC.CTA per warp and substep.
   static __device__ __forceinline__ void bar_arrive(int id, int count) {
-    __threadfence_block();
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
   }
   static __device__ __forceinline__ void bar_sync(int id, int count) {
