@@ -132,7 +132,7 @@ def test_diffusion_step_on_random_models(orc, tmp_path, seed):
     env, facts = _env(tmp_path, seed)
     dev = torch.device("cuda:0")
     raw = env.reset(prng.split(prng.PRNGKey(seed))[1]).pipeline_state.raw
-    H, n = 5, 96
+    H, n = 5, 128
     _, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, 20)
     e = eng.DiffusionEngine(env, n, H, 0.1, False, raw)
     key = np.uint32([7, seed])
@@ -147,3 +147,15 @@ def test_diffusion_step_on_random_models(orc, tmp_path, seed):
     scale = max(np.abs(ref["Ybar_im1"]).max(), 1e-6)
     assert np.abs(o.cpu().numpy() - ref["Ybar_im1"]).max() / scale < 1e-4
     assert abs(rew.item() - ref["rew_mean"]) <= 1e-4 * max(abs(ref["rew_mean"]), 1e-6) + 1e-6
+    # the same step sharded over two emulated ranks (64 samples each: whole runs -> the single-rank bits)
+    keys = np.zeros((20, 2), np.uint32); keys[12] = key
+    ranks = eng.DiffusionEngine.make_emulated_ranks(env, n, H, 0.1, False, raw, 2, Ndiffuse=20)
+    for r in ranks:
+        r.load_schedule(keys, sigmas, alphas, alphas_bar); r.set_step(12)
+        r.Ybars[12].copy_(torch.as_tensor(Ybar.reshape(-1), device=dev))
+    eng.DiffusionEngine.step_emulated_ranks(ranks)
+    torch.cuda.synchronize()
+    for r in ranks:
+        r.check_exchange()
+        assert_bit_exact(r.Ybars[11].cpu().numpy(), o.cpu().numpy(), f"seed {seed}: rank {r.rank} of 2 vs one rank")
+    assert_bit_exact(np.concatenate([r.rews_local.cpu().numpy() for r in ranks]), ref["rews"], f"seed {seed}: sharded returns")
