@@ -139,6 +139,14 @@ int mbd_test_arith(int op, const float* a_dev, const float* b_dev, float* out_de
 int mbd_update(const float* partials_dev, int P, int HNu, const float* Ybar_i_dev, const float coef[5],
                float* Ybar_im1_dev, mbd_stream s);
 
+/* pushT (/root/reference/mbd/envs/pushT.py:16-66, the reference's one env on Brax's `generalized` backend; planar
+ * reduced-coordinate pipeline restated in include/mbd_pusht.h).  params_dev [MBD_PT_NPARAM], x0_dev [16] = q | qd.
+ * key != NULL: fused sampling exactly as mbd_car2d_rollout.  final_state_dev [n,16], traj_dev [n,H,16] optional. */
+int mbd_pusht_rollout(const float* params_dev, const float* x0_dev, const uint32_t* key, int n_total, int n_begin,
+                      int n_local, int H, float sigma, const float* Ybar_dev, float* Y0s_dev, float* rewss_dev,
+                      float* rews_dev, float* final_state_dev, float* traj_dev, mbd_stream s);
+enum { MBD_ENV_CAR2D = 0, MBD_ENV_PUSHT = 1 };
+
 /* ---- one diffusion step as THREE parameterless launches (CUDA-graph capturable) -------------------------------------
  * reverse_once (mbd_planner.py:97-135) for any rank count: (1) sampling + rollouts, (2) global reward statistics /
  * demo blend / softmax in one 8-CTA thread-block cluster that pulls the peers' per-sample returns over NVLink itself,
@@ -158,7 +166,8 @@ typedef struct mbd_step_ctl {      /* 128 bytes, zero-initialised by the caller 
   uint32_t ticket[28];             /* "last CTA done" tickets: per column block, [27] over the column blocks... see step_tail.cuh */
 } mbd_step_ctl;
 typedef struct mbd_step_plan {
-  const mbd_model* model;            /* Brax-positional env; NULL = car2d (car_params_dev, state_init_dev = x0[3]) */
+  const mbd_model* model;            /* Brax-positional env; NULL = a flat-state env selected by env_kind: car2d (car_params_dev,
+                                      * state_init_dev = x0[3]) or pushT (car_params_dev = the MBD_PT_* table, state_init_dev = q|qd [16]) */
   const float* car_params_dev;
   const float* state_init_dev;       /* [L,13] */
   const mbd_step_params* params_dev; /* [Ndiffuse] */
@@ -169,6 +178,7 @@ typedef struct mbd_step_plan {
   float temp, rew_xref;
   const float* xref_dev;             /* demo reference (enable_demo) or NULL */
   int32_t href;
+  int32_t env_kind;                  /* model == NULL: MBD_ENV_CAR2D (0, the default) or MBD_ENV_PUSHT; sits in what was padding */
   float* Y0s_dev;                    /* [n_local, H*Nu] */
   float* rews_dev;                   /* [n_local]; P > 1: inside this rank's symmetric buffer at off_rews_words */
   float* logpd_dev;                  /* [n_local] or NULL; P > 1: at off_logpd_words */

@@ -35,7 +35,7 @@ class StepPlan(ctypes.Structure):
         ("Ybars_dev", c_vp), ("rew_hist_dev", c_vp),
         ("n_total", ctypes.c_int32), ("n_begin", ctypes.c_int32), ("n_local", ctypes.c_int32), ("H", ctypes.c_int32), ("nu", ctypes.c_int32),
         ("temp", ctypes.c_float), ("rew_xref", ctypes.c_float),
-        ("xref_dev", c_vp), ("href", ctypes.c_int32),
+        ("xref_dev", c_vp), ("href", ctypes.c_int32), ("env_kind", ctypes.c_int32),
         ("Y0s_dev", c_vp), ("rews_dev", c_vp), ("logpd_dev", c_vp), ("rews_all_dev", c_vp), ("logpd_all_dev", c_vp), ("logp_dev", c_vp),
         ("weights_dev", c_vp), ("runs_dev", c_vp), ("partial_dev", c_vp), ("scalars_dev", c_vp),
         ("P", ctypes.c_int32), ("rank", ctypes.c_int32),
@@ -47,6 +47,7 @@ class StepPlan(ctypes.Structure):
 
 STEP_PARAMS_WORDS = 8    # sizeof(mbd_step_params) / 4
 STEP_CTL_WORDS = 32      # sizeof(mbd_step_ctl) / 4
+ENV_CAR2D, ENV_PUSHT = 0, 1   # mbd_step_plan.env_kind (model == NULL)
 
 
 def lib():
@@ -78,6 +79,8 @@ def lib():
                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     L.mbd_car2d_rollout.argtypes = [c_vp, c_vp, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                     c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]
+    L.mbd_pusht_rollout.argtypes = [c_vp, c_vp, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     L.mbd_softmax_weights.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                       c_vp, c_vp, c_vp, c_vp]
     L.mbd_weighted_sum.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]
@@ -102,7 +105,7 @@ def lib():
 
 
 EXPORTS = ["mbd_set_kernel_variant", "mbd_set_prng_layout", "mbd_model_set_warp_order", "mbd_model_set_group_map", "mbd_set_group_stagger", "mbd_layout_info", "mbd_last_error", "mbd_device_count", "mbd_model_create", "mbd_model_destroy", "mbd_sample",
-           "mbd_rollout", "mbd_sample_rollout", "mbd_reverse_step", "mbd_car2d_rollout", "mbd_softmax_weights", "mbd_weighted_sum", "mbd_weighted_sum_runs", "mbd_weighted_sqerr_sum", "mbd_peer_gather", "mbd_test_arith", "mbd_update", "mbd_step_launch", "mbd_step_launch_ev", "mbd_event_create", "mbd_event_destroy", "mbd_event_record",
+           "mbd_rollout", "mbd_sample_rollout", "mbd_reverse_step", "mbd_car2d_rollout", "mbd_pusht_rollout", "mbd_softmax_weights", "mbd_weighted_sum", "mbd_weighted_sum_runs", "mbd_weighted_sqerr_sum", "mbd_peer_gather", "mbd_test_arith", "mbd_update", "mbd_step_launch", "mbd_step_launch_ev", "mbd_event_create", "mbd_event_destroy", "mbd_event_record",
            "mbd_event_sync", "mbd_event_elapsed_ms", "mbd_ffma_peak", "mbd_abi_sizes"]
 
 

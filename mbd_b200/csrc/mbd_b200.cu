@@ -723,6 +723,10 @@ __global__ void k_car2d(CarArgs a) {
   if (a.logpd && a.xref) a.logpd[i] = 0.0f - acc / (float)a.H;
 }
 
+}  // namespace mbd
+#include "pusht.cuh"   // k_pusht: the pushT env (planar generalized pipeline), uses sample_elem / clampf from above
+namespace mbd {
+
 // ---- test hook: the exact div / rcp / sqrt device sequences on arrays (tests/test_rollout_gpu.py) ----------
 __global__ void k_test_arith(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1461,6 +1465,24 @@ int mbd_car2d_rollout(const float* params_dev, const float* x0_dev, const uint32
   return MBD_OK;
 }
 
+int mbd_pusht_rollout(const float* params_dev, const float* x0_dev, const uint32_t* key, int n_total, int n_begin, int n_local, int H,
+                      float sigma, const float* Ybar_dev, float* Y0s_dev, float* rewss_dev, float* rews_dev, float* final_state_dev,
+                      float* traj_dev, mbd_stream s) {
+  if (!params_dev || !x0_dev || !Y0s_dev || !rews_dev || n_local <= 0 || H <= 0) return MBD_EINVAL;
+  if (key && (!Ybar_dev || n_begin < 0 || n_begin + n_local > n_total)) return MBD_EINVAL;
+  if (key && (uint64_t)n_total * (uint64_t)H * 2ull >= 0xffffffffull) return MBD_EINVAL;
+  mbd::PushTArgs a;
+  memset(&a, 0, sizeof(a));
+  a.params = params_dev; a.x0 = x0_dev; a.Y0s = Y0s_dev; a.n = n_local; a.H = H; a.rewss = rewss_dev; a.rews = rews_dev;
+  a.final_state = final_state_dev; a.traj = traj_dev;
+  a.fused = key != nullptr;
+  a.prng_part = g_prng_part;
+  if (key) { a.k0 = key[0]; a.k1 = key[1]; a.n_total = n_total; a.n_begin = n_begin; a.sigma = sigma; a.Ybar = Ybar_dev; }
+  mbd::k_pusht<<<(n_local + 63) / 64, 64, 0, (cudaStream_t)s>>>(a);
+  CK(cudaGetLastError());
+  return MBD_OK;
+}
+
 int mbd_softmax_weights(const float* rews_all_dev, const float* logpd_all_dev, int n_total, int n_begin, int n_local, float temp,
                         float rew_xref, float* weights_dev, float* scalars_dev, float* logp_scratch_dev, mbd_stream s) {
   if (!rews_all_dev || !weights_dev || !scalars_dev || !logp_scratch_dev || n_total <= 0 || n_begin < 0 || n_begin + n_local > n_total)
@@ -1580,6 +1602,16 @@ static int step_launch_impl(const mbd_step_plan* pl, cudaStream_t st, cudaEvent_
     a.sp = pl->params_dev; a.ctl = pl->ctl_dev; a.Ybars = pl->Ybars_dev;
     int rc = launch_rollout(true, a, pl->model, st);
     if (rc != MBD_OK) return rc;
+  } else if (pl->env_kind == MBD_ENV_PUSHT) {
+    if (!pl->car_params_dev || pl->nu != 2 || demo) return MBD_EINVAL;
+    mbd::PushTArgs a;
+    memset(&a, 0, sizeof(a));
+    a.params = pl->car_params_dev; a.x0 = pl->state_init_dev; a.Y0s = pl->Y0s_dev; a.n = pl->n_local; a.H = pl->H;
+    a.rews = pl->rews_dev;
+    a.fused = 1; a.n_total = pl->n_total; a.n_begin = pl->n_begin; a.prng_part = g_prng_part;
+    a.sp = pl->params_dev; a.ctl = pl->ctl_dev; a.Ybars = pl->Ybars_dev;
+    mbd::k_pusht<<<(pl->n_local + 63) / 64, 64, 0, st>>>(a);
+    CK(cudaGetLastError());
   } else {
     if (!pl->car_params_dev || pl->nu != 2) return MBD_EINVAL;
     mbd::CarArgs a;

@@ -42,6 +42,9 @@ class BraxLikeSystem:
         self.geom_size = size
         self.geom_rgba = np.tile(np.float32([0.8, 0.6, 0.4, 1.0]), (self.ngeom, 1))
         self.geom_rgba[self.geom_type == 0] = np.float32([0.5, 0.5, 0.5, 1.0])
+        for i, g in enumerate(geoms):           # models that carry their own colours (pushT: green pusher, blue T, red ghost)
+            if getattr(g, "rgba", None) is not None:
+                self.geom_rgba[i] = np.asarray(g.rgba, np.float32)
 
 
 def _tolist(a):

@@ -150,6 +150,24 @@ def car2d_rollout(params, x0, Y0s, xref=None, want_rewss=False, want_traj=False,
     return dict(rews=rews, rewss=rewss, logpd=logpd, traj=traj)
 
 
+def pusht_rollout(params, x0, Y0s, want_rewss=False, want_final=False, want_traj=False, key=None, n_total=0, n_begin=0,
+                  sigma=0.0, Ybar=None, rews_out=None):
+    """pushT rollouts (csrc/pusht.cuh); with `key` the noise is drawn in-kernel and written to Y0s [n,H,2]."""
+    params, x0, Y0s = _dev(params), _dev(x0), _dev(Y0s)
+    n, H, _ = Y0s.shape
+    dev = Y0s.device
+    rews = torch.empty(n, device=dev) if rews_out is None else rews_out
+    rewss = torch.empty((n, H), device=dev) if want_rewss else None
+    final = torch.empty((n, 16), device=dev) if want_final else None
+    traj = torch.empty((n, H, 16), device=dev) if want_traj else None
+    kp = None
+    if key is not None:
+        k, kp = key_ptr(key)
+    check(_lib.lib().mbd_pusht_rollout(_p(params), _p(x0), kp, n_total, n_begin, n, H, ctypes.c_float(sigma), _p(Ybar), _p(Y0s),
+                                       _p(rewss), _p(rews), _p(final), _p(traj), _stream()), "mbd_pusht_rollout")
+    return dict(rews=rews, rewss=rewss, final=final, traj=traj, logpd=None)
+
+
 def softmax_weights(rews_all, logpd_all, n_begin, n_local, temp, rew_xref, weights_out, scalars_out, scratch):
     n_total = rews_all.numel()
     check(_lib.lib().mbd_softmax_weights(_p(_dev(rews_all)), _p(logpd_all), n_total, n_begin, n_local, ctypes.c_float(temp),

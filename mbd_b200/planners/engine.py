@@ -144,6 +144,14 @@ class DiffusionEngine:
             x0 = state_init.pipeline_state if hasattr(state_init, "pipeline_state") else state_init
             self.state_init = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float32), device=d)
             self.xref = xref if self.enable_demo else None
+        elif env.kind == "pusht":
+            if self.enable_demo:
+                raise ValueError("pushT has no demonstration (mbd_planner.py:118 applies to humanoidtrack / car2d)")
+            self.model = None
+            self.params_car = env.device_params()
+            raw = state_init.pipeline_state.raw if hasattr(state_init, "pipeline_state") else state_init
+            self.state_init = torch.as_tensor(np.ascontiguousarray(raw, dtype=np.float32), device=d)
+            self.xref = None
         else:
             raise ValueError(env.kind)
         self.rew_xref = float(getattr(env, "rew_xref", 0.0))
@@ -160,6 +168,7 @@ class DiffusionEngine:
         p.n_total, p.n_begin, p.n_local, p.H, p.nu = self.N, self.n_begin, self.n_local, self.H, self.Nu
         p.temp, p.rew_xref = self.temp, self.rew_xref
         p.xref_dev = vp(self.xref)
+        p.env_kind = _lib.ENV_PUSHT if self.env.kind == "pusht" else _lib.ENV_CAR2D
         p.href = 0 if self.xref is None else int(self.xref.shape[1] if self.env.kind == "xpbd" else self.xref.shape[0])
         p.Y0s_dev, p.rews_dev, p.logpd_dev = vp(self.Y0s), vp(self.rews_local), vp(self.logpd_local)
         p.rews_all_dev, p.logpd_all_dev, p.logp_dev = vp(self.rews_all), vp(self.logpd_all), vp(self.logp_scratch)
@@ -252,6 +261,9 @@ class DiffusionEngine:
         if self.env.kind == "xpbd":
             ops.sample_rollout(self.model, self.state_init, key, self.N, self.n_begin, self.n_local, self.H, float(sigma), Ybar_i,
                                self.Y0s, self.rews_local, xref=self.xref, logpd_out=self.logpd_local)
+        elif self.env.kind == "pusht":
+            ops.pusht_rollout(self.params_car, self.state_init, self.Y0s.view(self.n_local, self.H, 2), key=key, n_total=self.N,
+                              n_begin=self.n_begin, sigma=float(sigma), Ybar=Ybar_i, rews_out=self.rews_local)
         else:
             ops.car2d_rollout(self.params_car, self.state_init, self.Y0s.view(self.n_local, self.H, 2), xref=self.xref, key=key,
                               n_total=self.N, n_begin=self.n_begin, sigma=float(sigma), Ybar=Ybar_i, rews_out=self.rews_local,

@@ -116,7 +116,7 @@ def run_diffusion(args: Args, log_every: int = 10, return_trajectory: bool = Fal
         np.save(f"{path}/mu_0ts.npy", Yi.cpu().numpy())
         if args.env_name == "car2d":
             _render_car2d(env, state_init, Yi[-1].cpu().numpy(), args, path)
-        elif env.kind == "xpbd":
+        elif env.kind in ("xpbd", "pusht"):
             # mbd_planner.py:168-178: rollout.html = brax.io.html.render(sys with opt.timestep = env.dt, rollout).  The same
             # page (and the JSON document inside it, which vis_diffusion.py / brax.io.html.render_from_json consume) is written
             # by mbd_b200.io.brax_json; rollout_states.npz keeps the plain arrays
@@ -139,6 +139,8 @@ def final_reward(env, engine: DiffusionEngine, us: torch.Tensor) -> float:
     us = us.reshape(1, engine.H, engine.Nu).contiguous()
     if env.kind == "xpbd":
         out = ops.rollout(engine.model, engine.state_init, us)
+    elif env.kind == "pusht":
+        out = ops.pusht_rollout(engine.params_car, engine.state_init, us)
     else:
         out = ops.car2d_rollout(engine.params_car, engine.state_init, us)
     return float(out["rews"][0].item())

@@ -26,7 +26,7 @@ def rollout_us(step_env, state, us):
         out = ops.car2d_rollout(params, torch.as_tensor(np.asarray(state.pipeline_state, np.float32), device=dev),
                                 torch.as_tensor(us[None], device=dev), want_rewss=True, want_traj=True)
         return out["rewss"][0].cpu().numpy(), list(out["traj"][0].cpu().numpy())
-    if env is not None and getattr(env, "kind", None) == "xpbd":
+    if env is not None and getattr(env, "kind", None) in ("xpbd", "pusht"):
         rews, states = [], []
         st = state
         # per-step states are needed by callers (rendering); one launch per step keeps them exact
@@ -82,7 +82,7 @@ def render_us(step_env, sys, state, us, dt=None):
     without world poses (car2d) the list of states is returned."""
     env = _env_of(step_env)
     rollout = rollout_states(step_env, state, us)
-    if env is not None and getattr(env, "kind", None) == "xpbd":
+    if env is not None and getattr(env, "kind", None) in ("xpbd", "pusht"):
         from .io import brax_json
         return brax_json.render(sys, rollout, env.dt if dt is None else dt)
     return rollout

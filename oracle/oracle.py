@@ -22,11 +22,11 @@ def build(force: bool = False) -> str:
     """Compiles oracle/libmbd_oracle.so (gcc, see oracle/Makefile) when it is missing, stale or forced."""
     import fcntl
     so = os.path.join(_HERE, "libmbd_oracle.so")
-    src = os.path.join(_HERE, "mbd_oracle.c")
-    hdrs = [os.path.join(_HERE, "..", "include", h) for h in ("mbd_fp32.h", "mbd_model.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("mbd_oracle.c", "pusht_oracle.c", "Makefile")]
+    hdrs = [os.path.join(_HERE, "..", "include", h) for h in ("mbd_fp32.h", "mbd_model.h", "mbd_pusht.h")]
 
     def stale():
-        return (not os.path.exists(so)) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in [src] + hdrs if os.path.exists(p))
+        return (not os.path.exists(so)) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in srcs + hdrs if os.path.exists(p))
 
     if force or stale():
         with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
@@ -234,6 +234,20 @@ def car2d_rollout(params, x0, Y0s, xref=None, want_rewss=False, want_traj=False,
     lib().orc_car2d_rollout(_fp(params), _fp(x0), _fp(Y0s), n, H, _fp(rewss), _fp(rews), _fp(xref), href, _fp(logpd),
                             _fp(traj), nthreads)
     return dict(rews=rews, rewss=rewss, logpd=logpd, traj=traj)
+
+
+def pusht_rollout(params, x0, Y0s, want_rewss=False, want_final=False, want_traj=False, nthreads=0):
+    """vmap(rollout_us) of the pushT env (oracle/pusht_oracle.c): params [MBD_PT_NPARAM], x0 [16] = q | qd, Y0s [n, H, 2]"""
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    x0 = np.ascontiguousarray(x0, dtype=np.float32).reshape(16)
+    Y0s = np.ascontiguousarray(Y0s, dtype=np.float32)
+    n, H, _ = Y0s.shape
+    rews = np.zeros(n, dtype=np.float32)
+    rewss = np.zeros((n, H), dtype=np.float32) if want_rewss else None
+    final = np.zeros((n, 16), dtype=np.float32) if want_final else None
+    traj = np.zeros((n, H, 16), dtype=np.float32) if want_traj else None
+    lib().orc_pusht_rollout(_fp(params), _fp(x0), _fp(Y0s), n, H, _fp(rewss), _fp(rews), _fp(final), _fp(traj), nthreads)
+    return dict(rews=rews, rewss=rewss, final=final, traj=traj, logpd=None)
 
 
 def fmap(fn: str, a, b=None):

@@ -66,7 +66,7 @@ def update(Ybar_i, Ybar, alphas, alphas_bar, i):
 
 
 class OracleEnv:
-    """Rollout backend for the oracle planner: kind 'xpbd' (blob, state) or 'car2d' (params, x0)."""
+    """Rollout backend for the oracle planner: kind 'xpbd' (blob, state), 'car2d' (params, x0) or 'pusht' (params, x0)."""
 
     def __init__(self, kind, Nu, **kw):
         self.kind, self.Nu, self.kw = kind, Nu, kw
@@ -80,6 +80,8 @@ class OracleEnv:
                 return out
         if self.kind == "xpbd":
             return orc.xpbd_rollout(self.kw["blob"], self.kw["state"], Y, xref=xref, nthreads=nthreads)
+        if self.kind == "pusht":
+            return orc.pusht_rollout(self.kw["params"], self.kw["x0"], Y, nthreads=nthreads)
         return orc.car2d_rollout(self.kw["params"], self.kw["x0"], Y, xref=xref, nthreads=nthreads)
 
 

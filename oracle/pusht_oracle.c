@@ -1,0 +1,232 @@
+/* pusht_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE, never on the product path) for the pushT env.
+ *
+ * Restates what /root/reference/mbd/envs/pushT.py:16-66 computes: `pipeline_step` of Brax's GENERALIZED backend
+ * (brax/generalized/pipeline.py::step — an un-vendored dependency of the reference, restated from the published algorithm
+ * [brax-recalled]) on the planar three-body model of /root/reference/mbd/assets/pushT.xml, plus the env's reward.
+ *
+ * PARITY UNPINNED: neither Brax nor JAX can be installed here, the reference holds no golden vectors for this env.  What is
+ * restated and how sure it is:
+ *   structure of a step            tau -> qf_smooth -> qf_constraint -> integrate                      [brax-recalled]
+ *   qf_smooth                      actuation + joint damping - centrifugal bias (RNE of a planar body)  [rigid-body mechanics]
+ *   soft constraints               MuJoCo solref (0.02, 1) / solimp (0.9, 0.95, 0.001, 0.5, 2):
+ *                                  imp(pos), aref = -b vel - k imp pos                                  [brax-recalled == MuJoCo docs]
+ *   constraint rows                joint limits; one sphere-box contact per box, 4-sided friction pyramid
+ *                                  n -+ mu t for t in the two tangents (the out-of-plane pair has no
+ *                                  in-plane Jacobian and acts as two more normal rows)                 [brax-recalled]
+ *   regulariser                    R = (1 - imp) / imp * diag(J M^-1 J^T): the EXACT diagonal where Brax
+ *                                  uses an inverse-weight approximation                                 [own choice]
+ *   constraint solve               projected Gauss-Seidel, MBD_PT_ITERS sweeps, on the QP
+ *                                  min 1/2 x^T (J M^-1 J^T + R) x + x^T (J M^-1 qf_smooth - aref), x >= 0;
+ *                                  A is SPD, the minimiser is unique, so any convergent solver agrees with
+ *                                  Brax's up to its truncation error                                   [own solver]
+ *   integration                    qd += dt (M + dt D)^-1 (qf_smooth + J^T x);  q += dt qd             [brax-recalled]
+ *   contact point                  midway between the two surfaces                                     [brax-recalled]
+ * All of it is fp32 with the contraction rules of include/mbd_fp32.h; the CUDA kernel (mbd_b200/csrc/pusht.cuh) is
+ * compared with this file bit for bit.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "mbd_fp32.h"
+#include "mbd_pusht.h"
+
+#define ORC_API __attribute__((visibility("default")))
+
+static inline float pt_clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+/* impedance and reference acceleration of one constraint row (MuJoCo solver parameters, power = 2) */
+static void pt_imp_aref(const float* P, float pos, float vel, float* imp, float* aref) {
+  const float dmin = P[MBD_PT_DMIN], dmax = P[MBD_PT_DMAX], mid = P[MBD_PT_MID];
+  float x = fabsf(pos) / P[MBD_PT_WIDTH];
+  float a = (1.0f / mid) * (x * x);
+  float omx = 1.0f - x;
+  float b = 1.0f - (1.0f / (1.0f - mid)) * (omx * omx);
+  float y = x < mid ? a : b;
+  float d = pt_clampf(dmin + y * (dmax - dmin), dmin, dmax);
+  if (x > 1.0f) d = dmax;
+  *imp = d;
+  *aref = (0.0f - P[MBD_PT_KB] * vel) - (P[MBD_PT_KK] * d) * pos;
+}
+
+typedef struct {
+  float J[MBD_PT_NROW][5]; /* pusher x, y | slider x, y, theta */
+  float pos[MBD_PT_NROW];
+  int active[MBD_PT_NROW];
+} pt_rows;
+
+/* one physics step; u = the two motor controls (already clipped) */
+static void pt_substep(const float* P, float* q, float* qd, const float* u) {
+  const float dt = P[MBD_PT_DT];
+  const float ms = P[MBD_PT_MS], ims = P[MBD_PT_IMS], Is = P[MBD_PT_IS], iIs = P[MBD_PT_IIS];
+  float s, c;
+  mbd_sincosf(q[4], &s, &c);
+  /* slider COM offset in the world frame, r = R(theta) c_body */
+  const float rx = c * P[MBD_PT_CX] - s * P[MBD_PT_CY];
+  const float ry = s * P[MBD_PT_CX] + c * P[MBD_PT_CY];
+  /* ---- qf_smooth = actuation + passive (joint damping) - bias (centrifugal term of the offset COM) */
+  float f[5];
+  const float w = qd[4], mw2 = ms * (w * w);
+  f[0] = P[MBD_PT_GEAR0] * u[0] - P[MBD_PT_DPX] * qd[0];
+  f[1] = P[MBD_PT_GEAR1] * u[1] - P[MBD_PT_DPY] * qd[1];
+  f[2] = mw2 * rx - P[MBD_PT_DSX] * qd[2];
+  f[3] = mw2 * ry - P[MBD_PT_DSY] * qd[3];
+  f[4] = 0.0f - P[MBD_PT_DSTH] * w;
+  /* ---- M^-1 of the slider block: M = [[m, 0, -m ry], [0, m, m rx], [-m ry, m rx, I + m |r|^2]]; its Schur complement is I */
+  const float A00 = ims + (ry * ry) * iIs, A01 = 0.0f - (rx * ry) * iIs, A02 = ry * iIs;
+  const float A11 = ims + (rx * rx) * iIs, A12 = 0.0f - rx * iIs, A22 = iIs;
+  /* ---- constraint rows */
+  pt_rows R;
+  memset(&R, 0, sizeof(R));
+  for (int k = 0; k < MBD_PT_NLIM; ++k) {
+    const float pmin = q[k] - P[MBD_PT_LIM0 + 2 * k], pmax = P[MBD_PT_LIM0 + 2 * k + 1] - q[k];
+    const float pm = pmin < pmax ? pmin : pmax;
+    R.pos[k] = pm < 0.0f ? pm : 0.0f;
+    R.active[k] = pm < 0.0f;
+    R.J[k][k] = pmin < pmax ? 1.0f : -1.0f;
+  }
+  const float mu = P[MBD_PT_MU], rp = P[MBD_PT_RP];
+  for (int b = 0; b < MBD_PT_NBOX; ++b) {
+    const float* B = P + MBD_PT_BOX0 + 4 * b;
+    const float bx = q[2] + (c * B[0] - s * B[1]), by = q[3] + (s * B[0] + c * B[1]);
+    const float dx = q[0] - bx, dy = q[1] - by;
+    const float lx = c * dx + s * dy, ly = c * dy - s * dx; /* sphere centre in the box frame */
+    const float clx = pt_clampf(lx, -B[2], B[2]), cly = pt_clampf(ly, -B[3], B[3]);
+    const float ex = lx - clx, ey = ly - cly;
+    const float d2 = ex * ex + ey * ey;
+    float nlx, nly, dist, sx = clx, sy = cly; /* normal (box -> sphere) and the box surface point, box frame */
+    if (d2 > 0.0f) {
+      const float d = sqrtf(d2);
+      nlx = ex / d; nly = ey / d;
+      dist = d - rp;
+    } else { /* centre inside the box: leave through the nearest face */
+      const float px = B[2] - fabsf(lx), py = B[3] - fabsf(ly);
+      if (px < py) { nlx = lx < 0.0f ? -1.0f : 1.0f; nly = 0.0f; dist = (0.0f - px) - rp; sx = nlx * B[2]; }
+      else { nlx = 0.0f; nly = ly < 0.0f ? -1.0f : 1.0f; dist = (0.0f - py) - rp; sy = nly * B[3]; }
+    }
+    const float nx = c * nlx - s * nly, ny = s * nlx + c * nly;
+    const float half = 0.5f * dist;
+    const float ax = B[0] + (sx + nlx * half), ay = B[1] + (sy + nly * half); /* contact point, body frame */
+    const float rhox = c * ax - s * ay, rhoy = s * ax + c * ay;                /* arm from the slider origin */
+    const float tx = 0.0f - ny, ty = nx;
+    const float dirs[4][2] = {{nx - mu * tx, ny - mu * ty}, {nx + mu * tx, ny + mu * ty}, {nx, ny}, {nx, ny}};
+    for (int j = 0; j < 4; ++j) {
+      const int r = MBD_PT_NLIM + 4 * b + j;
+      const float ddx = dirs[j][0], ddy = dirs[j][1];
+      R.J[r][0] = ddx; R.J[r][1] = ddy;
+      R.J[r][2] = 0.0f - ddx; R.J[r][3] = 0.0f - ddy;
+      R.J[r][4] = 0.0f - (rhox * ddy - rhoy * ddx);
+      R.pos[r] = dist;
+      R.active[r] = dist < 0.0f;
+    }
+  }
+  /* ---- constraint QP and projected Gauss-Seidel */
+  float MiJ[MBD_PT_NROW][5], Dg[MBD_PT_NROW], Rg[MBD_PT_NROW], bq[MBD_PT_NROW], x[MBD_PT_NROW];
+  float Mif[5];
+  const float imp_ = P[MBD_PT_IMP];
+  Mif[0] = imp_ * f[0]; Mif[1] = imp_ * f[1];
+  Mif[2] = (A00 * f[2] + A01 * f[3]) + A02 * f[4];
+  Mif[3] = (A01 * f[2] + A11 * f[3]) + A12 * f[4];
+  Mif[4] = (A02 * f[2] + A12 * f[3]) + A22 * f[4];
+  int any = 0;
+  for (int r = 0; r < MBD_PT_NROW; ++r) {
+    x[r] = 0.0f;
+    if (!R.active[r]) continue;
+    any = 1;
+    const float* J = R.J[r];
+    MiJ[r][0] = imp_ * J[0]; MiJ[r][1] = imp_ * J[1];
+    MiJ[r][2] = (A00 * J[2] + A01 * J[3]) + A02 * J[4];
+    MiJ[r][3] = (A01 * J[2] + A11 * J[3]) + A12 * J[4];
+    MiJ[r][4] = (A02 * J[2] + A12 * J[3]) + A22 * J[4];
+    const float arr = (((J[0] * MiJ[r][0] + J[1] * MiJ[r][1]) + J[2] * MiJ[r][2]) + J[3] * MiJ[r][3]) + J[4] * MiJ[r][4];
+    const float vel = (((J[0] * qd[0] + J[1] * qd[1]) + J[2] * qd[2]) + J[3] * qd[3]) + J[4] * qd[4];
+    float imp, aref;
+    pt_imp_aref(P, R.pos[r], vel, &imp, &aref);
+    Rg[r] = ((1.0f - imp) / imp) * arr;
+    Dg[r] = arr + Rg[r];
+    bq[r] = ((((J[0] * Mif[0] + J[1] * Mif[1]) + J[2] * Mif[2]) + J[3] * Mif[3]) + J[4] * Mif[4]) - aref;
+  }
+  float ftot[5] = {f[0], f[1], f[2], f[3], f[4]};
+  if (any) {
+    float acc[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}; /* M^-1 J^T x */
+    const int iters = (int)P[MBD_PT_ITERS];
+    for (int it = 0; it < iters; ++it)
+      for (int r = 0; r < MBD_PT_NROW; ++r) {
+        if (!R.active[r]) continue;
+        const float* J = R.J[r];
+        const float res = (((((J[0] * acc[0] + J[1] * acc[1]) + J[2] * acc[2]) + J[3] * acc[3]) + J[4] * acc[4]) + Rg[r] * x[r]) + bq[r];
+        float xn = x[r] - res / Dg[r];
+        xn = xn > 0.0f ? xn : 0.0f;
+        const float dxr = xn - x[r];
+        for (int k = 0; k < 5; ++k) acc[k] = acc[k] + MiJ[r][k] * dxr;
+        x[r] = xn;
+      }
+    for (int r = 0; r < MBD_PT_NROW; ++r)
+      if (R.active[r])
+        for (int k = 0; k < 5; ++k) ftot[k] = ftot[k] + R.J[r][k] * x[r];
+  }
+  /* ---- semi-implicit Euler, joint damping folded into the mass matrix: (M + dt D) qdd = ftot */
+  float qdd[5];
+  qdd[0] = ftot[0] / (P[MBD_PT_MP] + dt * P[MBD_PT_DPX]);
+  qdd[1] = ftot[1] / (P[MBD_PT_MP] + dt * P[MBD_PT_DPY]);
+  {
+    const float m1 = ms + dt * P[MBD_PT_DSX], m2 = ms + dt * P[MBD_PT_DSY];
+    const float a = 0.0f - ms * ry, b = ms * rx;
+    const float J3 = (Is + ms * (rx * rx + ry * ry)) + dt * P[MBD_PT_DSTH];
+    const float g1 = ftot[2] / m1, g2 = ftot[3] / m2;
+    const float den = (J3 - (a * a) / m1) - (b * b) / m2;
+    const float x3 = ((ftot[4] - a * g1) - b * g2) / den;
+    qdd[2] = g1 - (a * x3) / m1;
+    qdd[3] = g2 - (b * x3) / m2;
+    qdd[4] = x3;
+  }
+  for (int k = 0; k < 5; ++k) {
+    qd[k] = qd[k] + qdd[k] * dt;
+    q[k] = q[k] + qd[k] * dt;
+  }
+}
+
+/* pushT.py:50-62 */
+static float pt_reward(const float* q) {
+  const float gx = q[5] - q[2], gy = q[6] - q[3];
+  const float px = q[0] - q[2], py = q[1] - q[3];
+  const float dps = sqrtf(px * px + py * py) - 0.2f;
+  const float d_pusher2slider = dps > 0.0f ? dps : 0.0f;
+  return 1.0f - ((sqrtf(gx * gx + gy * gy) + fabsf(q[7] - q[4]) / MBD_PI_F) + d_pusher2slider);
+}
+
+/* params [MBD_PT_NPARAM]; x0 [16] = q | qd; Y0s [n, H, 2]; rewss [n, H] or NULL; rews [n]; final [n, 16] or NULL;
+ * traj [n, H, 16] or NULL (state after every env step) */
+ORC_API int orc_pusht_rollout(const float* params, const float* x0, const float* Y0s, int n, int H, float* rewss, float* rews,
+                              float* final_state, float* traj, int nthreads) {
+  const int nsub = (int)params[MBD_PT_NSUB];
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    float q[MBD_PT_NQ], qd[MBD_PT_NQ];
+    for (int k = 0; k < MBD_PT_NQ; ++k) { q[k] = x0[k]; qd[k] = x0[MBD_PT_NQ + k]; }
+    float sum = 0.0f;
+    for (int t = 0; t < H; ++t) {
+      const float* ur = Y0s + ((size_t)i * H + t) * 2;
+      const float u[2] = {pt_clampf(ur[0], -1.0f, 1.0f), pt_clampf(ur[1], -1.0f, 1.0f)}; /* motor ctrlrange */
+      for (int k = 0; k < nsub; ++k) pt_substep(params, q, qd, u);
+      const float r = pt_reward(q);
+      if (rewss) rewss[(size_t)i * H + t] = r;
+      sum += r;
+      if (traj) {
+        float* o = traj + ((size_t)i * H + t) * MBD_PT_STATE;
+        for (int k = 0; k < MBD_PT_NQ; ++k) { o[k] = q[k]; o[MBD_PT_NQ + k] = qd[k]; }
+      }
+    }
+    rews[i] = sum / (float)H;
+    if (final_state)
+      for (int k = 0; k < MBD_PT_NQ; ++k) { final_state[(size_t)i * MBD_PT_STATE + k] = q[k]; final_state[(size_t)i * MBD_PT_STATE + MBD_PT_NQ + k] = qd[k]; }
+  }
+  return 0;
+}

@@ -48,8 +48,8 @@ def test_env_registry():
     assert (hs.action_size, hs.observation_size, round(hs.dt, 6)) == (17, 47, 0.042)
     with pytest.raises(ValueError, match="Unknown environment"):
         mbd_b200.envs.get_env("nope")
-    with pytest.raises(NotImplementedError):
-        mbd_b200.envs.get_env("pushT")   # the one `generalized`-backend env
+    pt = mbd_b200.envs.get_env("pushT")   # the one `generalized`-backend env (tests/test_pusht.py)
+    assert (pt.action_size, pt.observation_size, round(pt.dt, 6), pt.backend) == (2, 16, 0.05, "generalized")
 
 
 def test_reset_is_the_reference_chain():

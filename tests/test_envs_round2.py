@@ -42,11 +42,9 @@ def _cpu_state(env, seed=0):
 # CPU: model compiler, registry, oracle physics
 # ---------------------------------------------------------------------------------------------------------------
 def test_registry_has_every_positional_env_of_the_reference():
-    """/root/reference/mbd/envs/__init__.py:13-33: every name resolves; pushT (generalized backend) explains itself"""
-    for name in NEW_ENVS + ["humanoidrun", "humanoidtrack", "humanoidstandup", "car2d"]:
+    """/root/reference/mbd/envs/__init__.py:13-33: every name resolves (pushT, the generalized-backend env, included)"""
+    for name in NEW_ENVS + ["humanoidrun", "humanoidtrack", "humanoidstandup", "car2d", "pushT"]:
         assert mbd_b200.envs.get_env(name) is not None
-    with pytest.raises(NotImplementedError, match="generalized"):
-        mbd_b200.envs.get_env("pushT")
     with pytest.raises(ValueError, match="Unknown environment"):
         mbd_b200.envs.get_env("nope")
 
