@@ -56,11 +56,17 @@ class Transform:
     pos: np.ndarray
     rot: np.ndarray
 
+    def replace(self, **kw):     # brax.base.Transform.replace (scripts/vis_diffusion.py:92-96 shifts x.pos for pushT with it)
+        return dataclasses.replace(self, **kw)
+
 
 @dataclasses.dataclass
 class Motion:
     ang: np.ndarray
     vel: np.ndarray
+
+    def replace(self, **kw):
+        return dataclasses.replace(self, **kw)
 
 
 @dataclasses.dataclass

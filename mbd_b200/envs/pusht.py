@@ -192,3 +192,26 @@ class PushT:
 
     def _get_done(self, pipeline_state) -> np.float32:
         return np.float32(self._get_reward(pipeline_state) > 0.95)                 # pushT.py:64-66
+
+
+def main():
+    """pushT.py:77-98: 50 uniformly random actions from the seed-1 reset, written as a Brax-visualizer page"""
+    import mbd_b200
+    from ..io import brax_json
+    env = PushT()
+    rng = prng.PRNGKey(1)
+    state = env.reset(rng)
+    rollout = [state.pipeline_state]
+    for _ in range(50):
+        rng, rng_act = prng.split(rng)
+        act = prng.uniform(rng_act, (env.action_size,), minval=-1.0, maxval=1.0)
+        state = env.step(state, act)
+        rollout.append(state.pipeline_state)
+    path = f"{mbd_b200.__path__[0]}/../results/pushT"
+    os.makedirs(path, exist_ok=True)
+    with open(f"{path}/vis.html", "w") as f:
+        f.write(brax_json.render(env.sys, rollout, env.dt))
+
+
+if __name__ == "__main__":
+    main()

@@ -170,6 +170,26 @@ def test_oracle_is_deterministic_and_sample_independent(env):
     np.testing.assert_allclose(a["rews"], a["rewss"].mean(axis=1), rtol=1e-6)
 
 
+def test_trajectory_export_document(env):
+    """the Brax-visualizer JSON document of a pushT rollout (mbd_planner.py:171-178 / vis_diffusion.py:27-112): three links, the
+    sphere and the four boxes with the colours of the XML, the table under "world", x.pos / x.rot stacked over time"""
+    from mbd_b200.io import brax_json
+    st = env.reset(prng.split(prng.PRNGKey(0))[1])
+    tr = _roll(env, st.pipeline_state.raw, np.tile([[0.0, 1.0]], (3, 1)))["traj"][0]
+    states = [st.pipeline_state] + [env.pipeline_init(r[:8], r[8:]) for r in tr]
+    doc = brax_json.to_dict(env.sys, states, env.dt)
+    assert doc["link_names"] == ["pusher", "slider", "goal"] and doc["opt"]["timestep"] == pytest.approx(0.05)
+    assert [g["name"] for g in doc["geoms"]["slider"]] == ["Box", "Box"] and doc["geoms"]["pusher"][0]["name"] == "Sphere"
+    assert doc["geoms"]["pusher"][0]["rgba"] == [0, 1, 0, 1] and doc["geoms"]["world"][0]["name"] == "Plane"
+    pos = np.asarray(doc["states"]["x"]["pos"]); rot = np.asarray(doc["states"]["x"]["rot"])
+    assert pos.shape == (4, 3, 3) and rot.shape == (4, 3, 4)
+    np.testing.assert_allclose(pos[:, 0, 1], [-0.15] + list(tr[:, 1]), atol=1e-6)
+    np.testing.assert_allclose(rot[0, 2], [np.cos(states[0].q[7] / 2), 0, 0, np.sin(states[0].q[7] / 2)], atol=1e-6)
+    # vis_diffusion.py:92-96 lifts every frame a little with x.replace(pos=...)
+    lifted = states[1].replace(x=states[1].x.replace(pos=states[1].x.pos + np.float32([0, 0, 0.01])))
+    assert lifted.x.pos[0, 2] == np.float32(0.01) and "<html>" in brax_json.render(env.sys, states, env.dt)
+
+
 # ---- GPU -----------------------------------------------------------------------------------------------------------
 def _T(a):
     import torch
