@@ -35,6 +35,50 @@ __device__ __forceinline__ void pt_imp_aref(const float* P, float pos, float vel
   aref = (0.0f - P[MBD_PT_KB] * vel) - (P[MBD_PT_KK] * d) * pos;
 }
 
+// the padded NRP x NRP constraint system and its projected Gauss-Seidel sweeps; for NRP = 4 and 8 every array below is indexed
+// by compile-time constants after unrolling, i.e. lives in registers
+template <int NRP>
+__device__ __forceinline__ void pt_solve(const float* P, const float (*J)[5], const float (*MiJ)[5], const float* Mif, const float* pos,
+                                         const int* idx, int nr, const float* qd, int iters, float* xout) {
+  float A[NRP][NRP], bq[NRP], invD[NRP], x[NRP];
+#pragma unroll
+  for (int i = 0; i < NRP; ++i) {
+    float Ji[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (i < nr) { const float* Jr = J[idx[i]]; Ji[0] = Jr[0]; Ji[1] = Jr[1]; Ji[2] = Jr[2]; Ji[3] = Jr[3]; Ji[4] = Jr[4]; }
+#pragma unroll
+    for (int j = 0; j < NRP; ++j) {
+      float a = 0.0f;
+      if (i < nr && j < nr) a = (((Ji[0] * MiJ[j][0] + Ji[1] * MiJ[j][1]) + Ji[2] * MiJ[j][2]) + Ji[3] * MiJ[j][3]) + Ji[4] * MiJ[j][4];
+      A[i][j] = a;
+    }
+    x[i] = 0.0f;
+    if (i < nr) {
+      const float vel = (((Ji[0] * qd[0] + Ji[1] * qd[1]) + Ji[2] * qd[2]) + Ji[3] * qd[3]) + Ji[4] * qd[4];
+      float imp, aref;
+      pt_imp_aref(P, pos[idx[i]], vel, imp, aref);
+      const float arr = A[i][i];
+      A[i][i] = arr + ((1.0f - imp) / imp) * arr;
+      invD[i] = 1.0f / A[i][i];
+      bq[i] = ((((Ji[0] * Mif[0] + Ji[1] * Mif[1]) + Ji[2] * Mif[2]) + Ji[3] * Mif[3]) + Ji[4] * Mif[4]) - aref;
+    } else {
+      A[i][i] = 1.0f; invD[i] = 1.0f; bq[i] = 0.0f;
+    }
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < NRP; ++i) {
+      float r0 = bq[i], r1 = 0.0f;   // two interleaved fused accumulators (even / odd columns): half the dependent chain
+#pragma unroll
+      for (int j = 0; j < NRP; j += 2) { r0 = fmaf(A[i][j], x[j], r0); r1 = fmaf(A[i][j + 1], x[j + 1], r1); }
+      const float res = r0 + r1;
+      const float xn = x[i] - res * invD[i];
+      x[i] = xn > 0.0f ? xn : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NRP; ++i) xout[i] = x[i];
+}
+
 // one brax.generalized.pipeline.step of the planar model; P = parameter table in shared memory
 __device__ void pusht_substep(const float* P, float* q, float* qd, float u0, float u1) {
   const float dt = P[MBD_PT_DT];
@@ -102,50 +146,34 @@ __device__ void pusht_substep(const float* P, float* q, float* qd, float u0, flo
       active[r] = dist < 0.0f;
     }
   }
-  // constraint QP + projected Gauss-Seidel
-  float MiJ[MBD_PT_NROW][5], Dg[MBD_PT_NROW], Rg[MBD_PT_NROW], bq[MBD_PT_NROW], x[MBD_PT_NROW];
+  // constraint QP + projected Gauss-Seidel: active rows compacted to the front, system padded with identity rows to 4 / 8 / 12
+  // rows (oracle/pusht_oracle.c does the same sums in the same order); the 4- and 8-row systems live in registers
+  float MiJ[MBD_PT_NROW][5];
   float Mif[5];
   const float imp_ = P[MBD_PT_IMP];
   Mif[0] = imp_ * f[0]; Mif[1] = imp_ * f[1];
   Mif[2] = (A00 * f[2] + A01 * f[3]) + A02 * f[4];
   Mif[3] = (A01 * f[2] + A11 * f[3]) + A12 * f[4];
   Mif[4] = (A02 * f[2] + A12 * f[3]) + A22 * f[4];
-  bool any = false;
-  for (int r = 0; r < MBD_PT_NROW; ++r) {
-    x[r] = 0.0f;
-    if (!active[r]) continue;
-    any = true;
-    const float* Jr = J[r];
-    MiJ[r][0] = imp_ * Jr[0]; MiJ[r][1] = imp_ * Jr[1];
-    MiJ[r][2] = (A00 * Jr[2] + A01 * Jr[3]) + A02 * Jr[4];
-    MiJ[r][3] = (A01 * Jr[2] + A11 * Jr[3]) + A12 * Jr[4];
-    MiJ[r][4] = (A02 * Jr[2] + A12 * Jr[3]) + A22 * Jr[4];
-    const float arr = (((Jr[0] * MiJ[r][0] + Jr[1] * MiJ[r][1]) + Jr[2] * MiJ[r][2]) + Jr[3] * MiJ[r][3]) + Jr[4] * MiJ[r][4];
-    const float vel = (((Jr[0] * qd[0] + Jr[1] * qd[1]) + Jr[2] * qd[2]) + Jr[3] * qd[3]) + Jr[4] * qd[4];
-    float imp, aref;
-    pt_imp_aref(P, pos[r], vel, imp, aref);
-    Rg[r] = ((1.0f - imp) / imp) * arr;
-    Dg[r] = arr + Rg[r];
-    bq[r] = ((((Jr[0] * Mif[0] + Jr[1] * Mif[1]) + Jr[2] * Mif[2]) + Jr[3] * Mif[3]) + Jr[4] * Mif[4]) - aref;
-  }
+  int idx[MBD_PT_NROW], nr = 0;
+  for (int r = 0; r < MBD_PT_NROW; ++r)
+    if (active[r]) idx[nr++] = r;
   float ftot[5] = {f[0], f[1], f[2], f[3], f[4]};
-  if (any) {
-    float acc[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  if (nr > 0) {
+    for (int i = 0; i < nr; ++i) {
+      const float* Jr = J[idx[i]];
+      MiJ[i][0] = imp_ * Jr[0]; MiJ[i][1] = imp_ * Jr[1];
+      MiJ[i][2] = (A00 * Jr[2] + A01 * Jr[3]) + A02 * Jr[4];
+      MiJ[i][3] = (A01 * Jr[2] + A11 * Jr[3]) + A12 * Jr[4];
+      MiJ[i][4] = (A02 * Jr[2] + A12 * Jr[3]) + A22 * Jr[4];
+    }
     const int iters = (int)P[MBD_PT_ITERS];
-    for (int it = 0; it < iters; ++it)
-      for (int r = 0; r < MBD_PT_NROW; ++r) {
-        if (!active[r]) continue;
-        const float* Jr = J[r];
-        const float res = (((((Jr[0] * acc[0] + Jr[1] * acc[1]) + Jr[2] * acc[2]) + Jr[3] * acc[3]) + Jr[4] * acc[4]) + Rg[r] * x[r]) + bq[r];
-        float xn = x[r] - res / Dg[r];
-        xn = xn > 0.0f ? xn : 0.0f;
-        const float dxr = xn - x[r];
-        for (int k = 0; k < 5; ++k) acc[k] = acc[k] + MiJ[r][k] * dxr;
-        x[r] = xn;
-      }
-    for (int r = 0; r < MBD_PT_NROW; ++r)
-      if (active[r])
-        for (int k = 0; k < 5; ++k) ftot[k] = ftot[k] + J[r][k] * x[r];
+    float x[MBD_PT_NROW];
+    if (nr <= 4) pt_solve<4>(P, J, MiJ, Mif, pos, idx, nr, qd, iters, x);
+    else if (nr <= 8) pt_solve<8>(P, J, MiJ, Mif, pos, idx, nr, qd, iters, x);
+    else pt_solve<12>(P, J, MiJ, Mif, pos, idx, nr, qd, iters, x);
+    for (int i = 0; i < nr; ++i)
+      for (int k = 0; k < 5; ++k) ftot[k] = ftot[k] + J[idx[i]][k] * x[i];
   }
   // (M + dt D) qdd = ftot
   float qdd[5];

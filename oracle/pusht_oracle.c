@@ -124,50 +124,65 @@ static void pt_substep(const float* P, float* q, float* qd, const float* u) {
       R.active[r] = dist < 0.0f;
     }
   }
-  /* ---- constraint QP and projected Gauss-Seidel */
-  float MiJ[MBD_PT_NROW][5], Dg[MBD_PT_NROW], Rg[MBD_PT_NROW], bq[MBD_PT_NROW], x[MBD_PT_NROW];
+  /* ---- constraint QP and projected Gauss-Seidel.  The active rows are compacted to the front and the system is padded with
+   * identity rows (x stays 0 there) to 4, 8 or 12 rows: the kernel keeps the 4- and 8-row systems in registers, and both sides
+   * sum the same padded terms in the same order. */
+  float MiJ[MBD_PT_NROW][5];
   float Mif[5];
   const float imp_ = P[MBD_PT_IMP];
   Mif[0] = imp_ * f[0]; Mif[1] = imp_ * f[1];
   Mif[2] = (A00 * f[2] + A01 * f[3]) + A02 * f[4];
   Mif[3] = (A01 * f[2] + A11 * f[3]) + A12 * f[4];
   Mif[4] = (A02 * f[2] + A12 * f[3]) + A22 * f[4];
-  int any = 0;
-  for (int r = 0; r < MBD_PT_NROW; ++r) {
-    x[r] = 0.0f;
-    if (!R.active[r]) continue;
-    any = 1;
-    const float* J = R.J[r];
-    MiJ[r][0] = imp_ * J[0]; MiJ[r][1] = imp_ * J[1];
-    MiJ[r][2] = (A00 * J[2] + A01 * J[3]) + A02 * J[4];
-    MiJ[r][3] = (A01 * J[2] + A11 * J[3]) + A12 * J[4];
-    MiJ[r][4] = (A02 * J[2] + A12 * J[3]) + A22 * J[4];
-    const float arr = (((J[0] * MiJ[r][0] + J[1] * MiJ[r][1]) + J[2] * MiJ[r][2]) + J[3] * MiJ[r][3]) + J[4] * MiJ[r][4];
-    const float vel = (((J[0] * qd[0] + J[1] * qd[1]) + J[2] * qd[2]) + J[3] * qd[3]) + J[4] * qd[4];
-    float imp, aref;
-    pt_imp_aref(P, R.pos[r], vel, &imp, &aref);
-    Rg[r] = ((1.0f - imp) / imp) * arr;
-    Dg[r] = arr + Rg[r];
-    bq[r] = ((((J[0] * Mif[0] + J[1] * Mif[1]) + J[2] * Mif[2]) + J[3] * Mif[3]) + J[4] * Mif[4]) - aref;
-  }
+  int idx[MBD_PT_NROW], nr = 0;
+  for (int r = 0; r < MBD_PT_NROW; ++r)
+    if (R.active[r]) idx[nr++] = r;
   float ftot[5] = {f[0], f[1], f[2], f[3], f[4]};
-  if (any) {
-    float acc[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}; /* M^-1 J^T x */
+  if (nr > 0) {
+    const int nrp = nr <= 4 ? 4 : (nr <= 8 ? 8 : 12);
+    float A[MBD_PT_NROW][MBD_PT_NROW], bq[MBD_PT_NROW], invD[MBD_PT_NROW], x[MBD_PT_NROW];
+    for (int i = 0; i < nr; ++i) {
+      const float* J = R.J[idx[i]];
+      MiJ[i][0] = imp_ * J[0]; MiJ[i][1] = imp_ * J[1];
+      MiJ[i][2] = (A00 * J[2] + A01 * J[3]) + A02 * J[4];
+      MiJ[i][3] = (A01 * J[2] + A11 * J[3]) + A12 * J[4];
+      MiJ[i][4] = (A02 * J[2] + A12 * J[3]) + A22 * J[4];
+    }
+    for (int i = 0; i < nrp; ++i)
+      for (int j = 0; j < nrp; ++j) {
+        float a = 0.0f;
+        if (i < nr && j < nr) {
+          const float* J = R.J[idx[i]];
+          a = (((J[0] * MiJ[j][0] + J[1] * MiJ[j][1]) + J[2] * MiJ[j][2]) + J[3] * MiJ[j][3]) + J[4] * MiJ[j][4];
+        }
+        A[i][j] = a;
+      }
+    for (int i = 0; i < nrp; ++i) {
+      x[i] = 0.0f;
+      if (i < nr) {
+        const float* J = R.J[idx[i]];
+        const float vel = (((J[0] * qd[0] + J[1] * qd[1]) + J[2] * qd[2]) + J[3] * qd[3]) + J[4] * qd[4];
+        float imp, aref;
+        pt_imp_aref(P, R.pos[idx[i]], vel, &imp, &aref);
+        const float arr = A[i][i];
+        A[i][i] = arr + ((1.0f - imp) / imp) * arr;
+        invD[i] = 1.0f / A[i][i];
+        bq[i] = ((((J[0] * Mif[0] + J[1] * Mif[1]) + J[2] * Mif[2]) + J[3] * Mif[3]) + J[4] * Mif[4]) - aref;
+      } else {
+        A[i][i] = 1.0f; invD[i] = 1.0f; bq[i] = 0.0f;
+      }
+    }
     const int iters = (int)P[MBD_PT_ITERS];
     for (int it = 0; it < iters; ++it)
-      for (int r = 0; r < MBD_PT_NROW; ++r) {
-        if (!R.active[r]) continue;
-        const float* J = R.J[r];
-        const float res = (((((J[0] * acc[0] + J[1] * acc[1]) + J[2] * acc[2]) + J[3] * acc[3]) + J[4] * acc[4]) + Rg[r] * x[r]) + bq[r];
-        float xn = x[r] - res / Dg[r];
-        xn = xn > 0.0f ? xn : 0.0f;
-        const float dxr = xn - x[r];
-        for (int k = 0; k < 5; ++k) acc[k] = acc[k] + MiJ[r][k] * dxr;
-        x[r] = xn;
+      for (int i = 0; i < nrp; ++i) {
+        float r0 = bq[i], r1 = 0.0f; /* two interleaved fused accumulators (even / odd columns): half the dependent chain */
+        for (int j = 0; j < nrp; j += 2) { r0 = fmaf(A[i][j], x[j], r0); r1 = fmaf(A[i][j + 1], x[j + 1], r1); }
+        const float res = r0 + r1;
+        const float xn = x[i] - res * invD[i];
+        x[i] = xn > 0.0f ? xn : 0.0f;
       }
-    for (int r = 0; r < MBD_PT_NROW; ++r)
-      if (R.active[r])
-        for (int k = 0; k < 5; ++k) ftot[k] = ftot[k] + R.J[r][k] * x[r];
+    for (int i = 0; i < nr; ++i)
+      for (int k = 0; k < 5; ++k) ftot[k] = ftot[k] + R.J[idx[i]][k] * x[i];
   }
   /* ---- semi-implicit Euler, joint damping folded into the mass matrix: (M + dt D) qdd = ftot */
   float qdd[5];
