@@ -96,6 +96,16 @@ def compare(dump_path: str, limit: int = 0):
         print("  normal(PRNGKey(0),(8,)) bit-equal:", bool(np.array_equal(np.float32(d["normal_key0"]).view(np.uint32), orc.normal(k0, (8,)).view(np.uint32))))
         print("  uniform(PRNGKey(0),(8,)) bit-equal:", bool(np.array_equal(np.float32(d["uniform_key0"]).view(np.uint32),
                                                                          prng.uniform(k0, (8,)).view(np.uint32))))
+    if "pusht_traj" in d:
+        print("== (4) pushT, generalized backend (oracle/pusht_oracle.c vs brax.generalized.pipeline) ==")
+        from oracle import oracle as orc
+        pt = mbd_b200.envs.get_env("pushT")
+        x0 = np.concatenate([np.float32(d["pusht_q0"]), np.zeros(8, np.float32)])
+        mine = orc.pusht_rollout(pt.params, x0, np.float32(d["pusht_actions"])[None], want_traj=True)["traj"][0]
+        err = np.abs(mine - np.float32(d["pusht_traj"]))
+        print(f"  max |q diff| = {err[:, :8].max():.3e}   max |qd diff| = {err[:, 8:].max():.3e}   (first env step: {err[0].max():.3e})")
+        print("  " + ("PINNED to 1e-3" if err.max() < 1e-3 else "NOT PINNED: the two declared own choices (solver, regulariser diagonal) or a "
+                                                          "[brax-recalled] item of oracle/pusht_oracle.c differ — see its header"))
     print("== (3) positional step, stage by stage, from the dump's own states ==")
     states, action = np.float32(d["states"]), np.float32(d["action"])     # [K+1, L, 13], [Nu]
     names = list(SWITCHES)
@@ -150,8 +160,24 @@ def make_dump(path: str, substeps: int, ref_assets: str):
     for _ in range(substeps):
         st = bpipe.step(sys_b, st, act)
         states.append(row(st))
+    # (4) pushT on the generalized backend (envs/pushT.py:16-20): q, qd after every env step of a scripted push
+    extra = {}
+    try:
+        from brax.generalized import pipeline as gpipe
+        sys_g = bmjcf.load(os.path.join(ref_assets, "pushT.xml"))
+        q0 = np.zeros(8, np.float32); q0[:2] = [-0.21, 0.0]; q0[5:] = [-0.4, 0.4, np.pi]
+        acts = np.float32([[1.0, 0.0]] * 4 + [[0.3, 0.8]] * 4 + [[-0.5, 0.2]] * 4)
+        sg = gpipe.init(sys_g, jp.asarray(q0), jp.zeros(8))
+        traj = []
+        for a in acts:
+            for _ in range(5):                                 # n_frames = 5
+                sg = gpipe.step(sys_g, sg, jp.asarray(a))
+            traj.append(np.concatenate([np.asarray(sg.q), np.asarray(sg.qd)]))
+        extra = dict(pusht_q0=q0, pusht_actions=acts, pusht_traj=np.float32(traj))
+    except Exception as e:  # noqa: BLE001
+        print(f"pushT section skipped: {e}")
     k0 = jax.random.PRNGKey(0)
-    np.savez(path, states=np.float32(states), action=np.float32(act), mass=np.asarray(sys_b.link.inertia.mass),
+    np.savez(path, **extra, states=np.float32(states), action=np.float32(act), mass=np.asarray(sys_b.link.inertia.mass),
              com=np.asarray(sys_b.link.inertia.transform.pos), init_q=np.asarray(sys_b.init_q),
              split_key0=np.asarray(jax.random.split(k0)), normal_key0=np.asarray(jax.random.normal(k0, (8,))),
              uniform_key0=np.asarray(jax.random.uniform(k0, (8,))),
@@ -175,7 +201,13 @@ def self_test():
         for _ in range(12):
             states.append(step_states(lib, env.blob, np.stack([states[-1]]), action)[0])
         path = os.path.join(tmp, "dump.npz")
-        np.savez(path, states=np.float32(states), action=action)
+        # a pushT trajectory from the oracle itself exercises section (4) of the comparison (difference exactly 0)
+        from oracle import oracle as orc
+        pt = mbd_b200.envs.get_env("pushT")
+        q0 = np.zeros(8, np.float32); q0[:2] = [-0.21, 0.0]; q0[5:] = [-0.4, 0.4, np.pi]
+        acts = np.float32([[1.0, 0.0]] * 4 + [[0.3, 0.8]] * 4)
+        ptraj = orc.pusht_rollout(pt.params, np.concatenate([q0, np.zeros(8, np.float32)]), acts[None], want_traj=True)["traj"][0]
+        np.savez(path, states=np.float32(states), action=action, pusht_q0=q0, pusht_actions=acts, pusht_traj=ptraj)
         SW = dict(SWITCHES)
         for k in list(SWITCHES):
             if k not in ("ORC_SINKING_GATE", "ORC_CONTACT_MIDPOINT", "ORC_TANGENT_EPS_FORM"):
