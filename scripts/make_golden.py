@@ -18,6 +18,24 @@ from oracle import planner as opl  # noqa: E402
 G = os.path.join(ROOT, "tests", "golden")
 os.makedirs(G, exist_ok=True)
 
+def pusht():
+    """pushT: a scripted push (contact with both boxes of the T, friction, a joint limit) and 24 sampled rollouts"""
+    pt = mbd_b200.envs.get_env("pushT")
+    x0 = pt.reset(prng.split(prng.PRNGKey(0))[1]).pipeline_state.raw
+    Y = np.clip(np.random.default_rng(12).normal(size=(24, 40, 2)).astype(np.float32) * 0.8 + np.float32([-0.2, 0.5]), -1.5, 1.5)
+    o = orc.pusht_rollout(pt.params, x0, Y, want_rewss=True, want_final=True)
+    x1 = x0.copy(); x1[0:2] = [-0.21, 0.0]
+    script = np.float32([[1.0, 0.0]] * 14 + [[0.2, 1.0]] * 10 + [[-1.0, -0.3]] * 6)
+    s_ = orc.pusht_rollout(pt.params, x1, script[None], want_traj=True, want_rewss=True)
+    np.savez_compressed(os.path.join(G, "pusht_oracle.npz"), params=pt.params, x0=x0, Y0s=Y, rews=o["rews"], rewss=o["rewss"], final=o["final"],
+                        x1=x1, script=script, script_traj=s_["traj"][0], script_rewss=s_["rewss"][0])
+    print("pushT rews", o["rews"][:4], "scripted push: slider ends at", s_["traj"][0][-1][2:5])
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "pusht":
+    pusht()
+    sys.exit(0)
+
 # ---- humanoidrun: 32 samples x 50 steps from the planner's own seed-0 chain --------------------------
 env = mbd_b200.envs.get_env("humanoidrun")
 rng, rng_reset = prng.split(prng.PRNGKey(0))
@@ -52,3 +70,4 @@ np.savez_compressed(os.path.join(G, "car2d_oracle.npz"), rew_final=np.float32(rf
                     rew_final_demo=np.float32(rfd), Yi_last_demo=Yid[-1], rews_demo=rewsd,
                     Yi_short_demo=Yis, rews_short_demo=rewss_)
 print("car2d", rf, rfd)
+pusht()

@@ -190,6 +190,18 @@ def test_trajectory_export_document(env):
     assert lifted.x.pos[0, 2] == np.float32(0.01) and "<html>" in brax_json.render(env.sys, states, env.dt)
 
 
+def test_oracle_matches_the_committed_fixture(env):
+    """tests/golden/pusht_oracle.npz (scripts/make_golden.py pusht): pins the oracle against accidental change"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pusht_oracle.npz"))
+    assert_bit_exact(env.params, g["params"], "parameter table")
+    o = orc.pusht_rollout(env.params, g["x0"], g["Y0s"], want_rewss=True, want_final=True)
+    assert_bit_exact(o["rews"], g["rews"]); assert_bit_exact(o["rewss"], g["rewss"]); assert_bit_exact(o["final"], g["final"])
+    s_ = orc.pusht_rollout(env.params, g["x1"], g["script"][None], want_traj=True, want_rewss=True)
+    assert_bit_exact(s_["traj"][0], g["script_traj"]); assert_bit_exact(s_["rewss"][0], g["script_rewss"])
+    tr = g["script_traj"]
+    assert tr[:, 2].max() > 0.9 and np.abs(tr[:, 4]).max() > 1.0, "the scripted push drives the slider to its limit and spins it"
+
+
 # ---- GPU -----------------------------------------------------------------------------------------------------------
 def _T(a):
     import torch
@@ -269,3 +281,15 @@ def test_run_diffusion_pushT_short(tmp_path, monkeypatch, capsys):
     st = env.reset(prng.split(prng.PRNGKey(args.seed))[1]).pipeline_state.raw
     zero = orc.pusht_rollout(env.params, st, np.zeros((1, 40, 2), np.float32))["rews"][0]
     assert np.isfinite(rew) and rew >= zero - 1e-3
+
+
+@pytest.mark.gpu
+def test_kernel_matches_the_committed_fixture(env):
+    """the CUDA path against tests/golden/pusht_oracle.npz (no oracle involved on the GPU box)"""
+    from mbd_b200 import ops
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pusht_oracle.npz"))
+    o = ops.pusht_rollout(_T(g["params"]), _T(g["x0"]), _T(g["Y0s"]), want_rewss=True, want_final=True)
+    for k in ("rews", "rewss", "final"):
+        assert_bit_exact(o[k].cpu().numpy(), g[k], f"pushT golden {k}")
+    s_ = ops.pusht_rollout(_T(g["params"]), _T(g["x1"]), _T(g["script"][None]), want_traj=True, want_rewss=True)
+    assert_bit_exact(s_["traj"][0].cpu().numpy(), g["script_traj"]); assert_bit_exact(s_["rewss"][0].cpu().numpy(), g["script_rewss"])
