@@ -34,6 +34,19 @@ if which in ("all", "rollout"):
         a = o if a is None else a
         print("hopper variant", v, "bit-identical:", bool(np.array_equal(o, a)), flush=True)
     ops.set_kernel_variant(0)
+if which in ("all", "rollout", "pusht"):
+    # pushT kernel (one sample per thread, constraint rows and the padded solver systems in registers / local memory): a scripted
+    # push that touches both boxes (8-row system) plus random actions, and two diffusion steps through the step API
+    pt = mbd_b200.envs.get_env("pushT")
+    x0 = pt.reset(prng.split(prng.PRNGKey(0))[1]).pipeline_state.raw.copy(); x0[0:2] = [-0.21, 0.0]
+    pu = np.clip(np.random.default_rng(2).normal(size=(70, 8, 2)) * 0.8 + [0.6, 0.1], -1.5, 1.5).astype(np.float32)
+    o = ops.pusht_rollout(pt.device_params(), torch.as_tensor(x0, device="cuda:0"), torch.as_tensor(pu, device="cuda:0"), want_final=True, want_traj=True)
+    print("pushT rollouts finite:", bool(torch.isfinite(o["final"]).all().item()), "slider moved:", float(o["final"][:, 2].abs().max().item()), flush=True)
+    _, al, ab, sg = eng.make_schedule(1e-4, 1e-2, 6)
+    ep = eng.DiffusionEngine(pt, 128, 8, 0.2, False, x0, Ndiffuse=6)
+    ep.load_schedule(eng.key_chain(np.uint32([3, 4]), 6), sg, al, ab); ep.set_step(5)
+    ep.step(); ep.step(); torch.cuda.synchronize()
+    print("pushT steps done, ctl.i =", int(ep.ctl[0].item()), flush=True)
 if which in ("all", "step"):
     Nd = 6
     _, alphas, alphas_bar, sigmas = eng.make_schedule(1e-4, 1e-2, Nd)
