@@ -22,7 +22,8 @@
 #define MBD_PT_NU 2
 #define MBD_PT_NBOX 2
 #define MBD_PT_NLIM 4      /* limited slide dofs: q0 q1 (pusher), q2 q3 (slider) */
-#define MBD_PT_NROW (MBD_PT_NLIM + 4 * MBD_PT_NBOX)
+#define MBD_PT_NCROW 3     /* rows per contact: n - mu t, n + mu t, and the out-of-plane pyramid pair merged into one n row */
+#define MBD_PT_NROW (MBD_PT_NLIM + MBD_PT_NCROW * MBD_PT_NBOX)
 
 enum {
   MBD_PT_DT = 0,    /* physics step (option timestep) */
@@ -38,6 +39,7 @@ enum {
   MBD_PT_MU = MBD_PT_BOX0 + 4 * MBD_PT_NBOX,                     /* friction coefficient of the pair */
   MBD_PT_DMIN, MBD_PT_DMAX, MBD_PT_WIDTH, MBD_PT_MID,            /* solimp (power must be 2) */
   MBD_PT_KB, MBD_PT_KK,                                          /* solref: b = 2/(dmax tc), k = 1/(dmax^2 tc^2 dr^2) */
+  MBD_PT_TOL,       /* solver: stop after a sweep that moves the constraint force J^T x by <= TOL * its largest component */
   MBD_PT_NPARAM
 };
 

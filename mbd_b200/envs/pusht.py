@@ -17,7 +17,7 @@ from .base import ASSET_DIR, Motion, State, Transform
 
 # include/mbd_pusht.h
 PT = dict(DT=0, NSUB=1, ITERS=2, GEAR0=3, GEAR1=4, MP=5, IMP=6, RP=7, DPX=8, DPY=9, MS=10, IMS=11, IS=12, IIS=13, CX=14, CY=15,
-          DSX=16, DSY=17, DSTH=18, LIM0=19, BOX0=27, MU=35, DMIN=36, DMAX=37, WIDTH=38, MID=39, KB=40, KK=41, NPARAM=42)
+          DSX=16, DSY=17, DSTH=18, LIM0=19, BOX0=27, MU=35, DMIN=36, DMAX=37, WIDTH=38, MID=39, KB=40, KK=41, TOL=42, NPARAM=43)
 
 
 @dataclasses.dataclass
@@ -110,6 +110,7 @@ def pack_params(model: dict, n_frames: int) -> np.ndarray:
     P[PT["DMIN"]], P[PT["DMAX"]], P[PT["WIDTH"]], P[PT["MID"]] = dmin, dmax, width, mid
     P[PT["KB"]] = 2.0 / (dmax * tc)
     P[PT["KK"]] = 1.0 / (dmax * dmax * tc * tc * dr * dr)
+    P[PT["TOL"]] = 1e-6     # solver tolerance (own choice, like the solver): well below the softness of the constraints themselves
     return P.astype(np.float32)
 
 

@@ -11,11 +11,13 @@
  *   soft constraints               MuJoCo solref (0.02, 1) / solimp (0.9, 0.95, 0.001, 0.5, 2):
  *                                  imp(pos), aref = -b vel - k imp pos                                  [brax-recalled == MuJoCo docs]
  *   constraint rows                joint limits; one sphere-box contact per box, 4-sided friction pyramid
- *                                  n -+ mu t for t in the two tangents (the out-of-plane pair has no
- *                                  in-plane Jacobian and acts as two more normal rows)                 [brax-recalled]
+ *                                  n -+ mu t for t in the two tangents [brax-recalled]; the out-of-plane pair has
+ *                                  the in-plane Jacobian n twice and is merged into ONE row with half the
+ *                                  regulariser (same QP minimiser, well-conditioned for Gauss-Seidel)   [own choice]
  *   regulariser                    R = (1 - imp) / imp * diag(J M^-1 J^T): the EXACT diagonal where Brax
  *                                  uses an inverse-weight approximation                                 [own choice]
- *   constraint solve               projected Gauss-Seidel, MBD_PT_ITERS sweeps, on the QP
+ *   constraint solve               projected Gauss-Seidel, at most MBD_PT_ITERS sweeps, stopped when a sweep moves the
+ *                                  constraint force J^T x by no more than MBD_PT_TOL (1e-6) of its largest component, on the QP
  *                                  min 1/2 x^T (J M^-1 J^T + R) x + x^T (J M^-1 qf_smooth - aref), x >= 0;
  *                                  A is SPD, the minimiser is unique, so any convergent solver agrees with
  *                                  Brax's up to its truncation error                                   [own solver]
@@ -56,6 +58,7 @@ static void pt_imp_aref(const float* P, float pos, float vel, float* imp, float*
 typedef struct {
   float J[MBD_PT_NROW][5]; /* pusher x, y | slider x, y, theta */
   float pos[MBD_PT_NROW];
+  float rscale[MBD_PT_NROW]; /* regulariser weight: 1, or 1/2 for a row that stands for two identical pyramid rows */
   int active[MBD_PT_NROW];
 } pt_rows;
 
@@ -88,6 +91,7 @@ static void pt_substep(const float* P, float* q, float* qd, const float* u) {
     R.pos[k] = pm < 0.0f ? pm : 0.0f;
     R.active[k] = pm < 0.0f;
     R.J[k][k] = pmin < pmax ? 1.0f : -1.0f;
+    R.rscale[k] = 1.0f;
   }
   const float mu = P[MBD_PT_MU], rp = P[MBD_PT_RP];
   for (int b = 0; b < MBD_PT_NBOX; ++b) {
@@ -113,21 +117,25 @@ static void pt_substep(const float* P, float* q, float* qd, const float* u) {
     const float ax = B[0] + (sx + nlx * half), ay = B[1] + (sy + nly * half); /* contact point, body frame */
     const float rhox = c * ax - s * ay, rhoy = s * ax + c * ay;                /* arm from the slider origin */
     const float tx = 0.0f - ny, ty = nx;
-    const float dirs[4][2] = {{nx - mu * tx, ny - mu * ty}, {nx + mu * tx, ny + mu * ty}, {nx, ny}, {nx, ny}};
-    for (int j = 0; j < 4; ++j) {
-      const int r = MBD_PT_NLIM + 4 * b + j;
+    /* the 4-sided pyramid: n -+ mu t (in plane) and n -+ mu z.  The out-of-plane pair has the SAME in-plane Jacobian n: two
+     * identical rows with regulariser R each are, for the QP, one row with regulariser R/2 carrying the sum of the two
+     * multipliers — merged here, because Gauss-Seidel converges at rate ~imp (0.9-0.95 per sweep) on the duplicated pair. */
+    const float dirs[MBD_PT_NCROW][2] = {{nx - mu * tx, ny - mu * ty}, {nx + mu * tx, ny + mu * ty}, {nx, ny}};
+    for (int j = 0; j < MBD_PT_NCROW; ++j) {
+      const int r = MBD_PT_NLIM + MBD_PT_NCROW * b + j;
       const float ddx = dirs[j][0], ddy = dirs[j][1];
       R.J[r][0] = ddx; R.J[r][1] = ddy;
       R.J[r][2] = 0.0f - ddx; R.J[r][3] = 0.0f - ddy;
       R.J[r][4] = 0.0f - (rhox * ddy - rhoy * ddx);
       R.pos[r] = dist;
+      R.rscale[r] = j == 2 ? 0.5f : 1.0f;
       R.active[r] = dist < 0.0f;
     }
   }
   /* ---- constraint QP and projected Gauss-Seidel.  The active rows are compacted to the front and the system is padded with
    * identity rows (x stays 0 there) to 4, 8 or 12 rows: the kernel keeps the 4- and 8-row systems in registers, and both sides
    * sum the same padded terms in the same order. */
-  float MiJ[MBD_PT_NROW][5];
+  float MiJ[12][5];
   float Mif[5];
   const float imp_ = P[MBD_PT_IMP];
   Mif[0] = imp_ * f[0]; Mif[1] = imp_ * f[1];
@@ -140,7 +148,7 @@ static void pt_substep(const float* P, float* q, float* qd, const float* u) {
   float ftot[5] = {f[0], f[1], f[2], f[3], f[4]};
   if (nr > 0) {
     const int nrp = nr <= 4 ? 4 : (nr <= 8 ? 8 : 12);
-    float A[MBD_PT_NROW][MBD_PT_NROW], bq[MBD_PT_NROW], invD[MBD_PT_NROW], x[MBD_PT_NROW];
+    float A[12][12], bq[12], invD[12], x[12]; /* padded sizes: 4, 8 or 12 >= MBD_PT_NROW */
     for (int i = 0; i < nr; ++i) {
       const float* J = R.J[idx[i]];
       MiJ[i][0] = imp_ * J[0]; MiJ[i][1] = imp_ * J[1];
@@ -165,7 +173,7 @@ static void pt_substep(const float* P, float* q, float* qd, const float* u) {
         float imp, aref;
         pt_imp_aref(P, R.pos[idx[i]], vel, &imp, &aref);
         const float arr = A[i][i];
-        A[i][i] = arr + ((1.0f - imp) / imp) * arr;
+        A[i][i] = arr + (R.rscale[idx[i]] * ((1.0f - imp) / imp)) * arr;
         invD[i] = 1.0f / A[i][i];
         bq[i] = ((((J[0] * Mif[0] + J[1] * Mif[1]) + J[2] * Mif[2]) + J[3] * Mif[3]) + J[4] * Mif[4]) - aref;
       } else {
@@ -173,14 +181,33 @@ static void pt_substep(const float* P, float* q, float* qd, const float* u) {
       }
     }
     const int iters = (int)P[MBD_PT_ITERS];
-    for (int it = 0; it < iters; ++it)
+    /* Convergence is judged on the generalized constraint FORCE J^T x, not on x: the rows of one contact are linearly dependent
+     * (n is the mean of n - mu t and n + mu t), so x keeps redistributing along the null space of J^T at rate ~imp per sweep long
+     * after the force — the only thing the dynamics sees — has converged. */
+    const float tol = P[MBD_PT_TOL];
+    float F[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    for (int it = 0; it < iters; ++it) {
+      float dF[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
       for (int i = 0; i < nrp; ++i) {
         float r0 = bq[i], r1 = 0.0f; /* two interleaved fused accumulators (even / odd columns): half the dependent chain */
         for (int j = 0; j < nrp; j += 2) { r0 = fmaf(A[i][j], x[j], r0); r1 = fmaf(A[i][j + 1], x[j + 1], r1); }
         const float res = r0 + r1;
         const float xn = x[i] - res * invD[i];
-        x[i] = xn > 0.0f ? xn : 0.0f;
+        const float xc = xn > 0.0f ? xn : 0.0f;
+        const float dxi = xc - x[i];
+        if (i < nr)
+          for (int k = 0; k < 5; ++k) dF[k] = fmaf(R.J[idx[i]][k], dxi, dF[k]);
+        x[i] = xc;
       }
+      float dmax = 0.0f, fmx = 0.0f;
+      for (int k = 0; k < 5; ++k) {
+        dmax = fmaxf(dmax, fabsf(dF[k]));
+        F[k] = F[k] + dF[k];
+        fmx = fmaxf(fmx, fabsf(F[k]));
+      }
+      /* the force moved by at most TOL of its largest component (TOL = 0: no change at all) */
+      if (dmax <= tol * fmx) break;
+    }
     for (int i = 0; i < nr; ++i)
       for (int k = 0; k < 5; ++k) ftot[k] = ftot[k] + R.J[idx[i]][k] * x[i];
   }
