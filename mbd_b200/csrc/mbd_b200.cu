@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(32 * kPkLinks, 1) k_rollout_pk(RolloutArgs a) 
     s.v = pk::mkV(b(10), b(11), b(12));
   }
   S.put_p(l, s.p); S.put_q(l, s.q); S.put_w(l, s.w);
-  typename std::conditional<SYNC == 2, SyncNamed, SyncGroup<kPkLinks>>::type Y;
+  typename std::conditional<SYNC == 2, SyncNamedFenced, SyncGroup<kPkLinks>>::type Y;
   if constexpr (SYNC == 2) Y.setup(Ms, l, L);
   else { Y.base = 1; Y.count_x = a.count_x; }
   int my_track = -1;

@@ -147,13 +147,21 @@ struct SyncGroup {
 //   pose id : the node bar.arrive's, each child bar.sync's      (count = 32 * (1 + nchildren))
 //   terms id: each child bar.arrive's, the node bar.sync's      (same count)
 // Needs 2 * (#nodes with children) <= 15; otherwise the caller falls back to SyncCta.
-struct SyncNamed {
+template <bool FENCE>
+struct SyncNamedT {
   int my_pose_id, my_terms_id, my_count;       // valid when this link has children (else 0)
   int par_pose_id, par_terms_id, par_count;    // ids owned by the parent (0 when parent is the world / none)
   // No fence before the arrival: bar.arrive / bar.sync order the arriving thread's earlier shared-memory accesses before the
   // barrier completes for every participant (the PTX ISA's own producer / consumer example is st.shared; bar.arrive on one side,
   // bar.sync; ld.shared on the other).  Round 1 had a __threadfence_block() here = four MEMBAR.SC.CTA per warp and substep.
+  // FENCE: A/B on one box (scripts/gpu_fence_ab.py, profiles/r02_experiments.md): without the fence the scalar kernel is 1.5 % faster
+  // (0.8535 vs 0.8665 ms at 4096 samples), the packed kernel 0.3 % slower (1.2051 vs 1.2016 ms at 8192) — each gets what suits it.
   static __device__ __forceinline__ void bar_arrive(int id, int count) {
+#ifdef MBD_NAMED_FENCE   // the A/B switch: force the fence everywhere
+    __threadfence_block();
+#else
+    if (FENCE) __threadfence_block();
+#endif
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
   }
   static __device__ __forceinline__ void bar_sync(int id, int count) {
@@ -200,6 +208,8 @@ struct SyncNamed {
     return 2 * nparents <= 15;
   }
 };
+using SyncNamed = SyncNamedT<false>;        // scalar warp-per-link kernels
+using SyncNamedFenced = SyncNamedT<true>;   // packed kernel
 
 // One brax.positional.pipeline.step for (link = this warp, sample = this lane).
 // All threads of the CTA must call.
