@@ -39,6 +39,15 @@
 
 #define ORC_API __attribute__((visibility("default")))
 
+/* Variant switches for the day a Brax install can be compared (scripts/pin_against_brax.py builds the grid with `make variant`).
+ * The defaults are what the CUDA kernel implements; every other value is a candidate reading of Brax [brax-recalled]. */
+#ifndef ORC_PT_REG_INVWEIGHT   /* 1: regulariser from MuJoCo-style inverse weights at qpos0 instead of the exact diagonal:        */
+#define ORC_PT_REG_INVWEIGHT 0 /*    limits R = w_dof (1-imp)/imp; pyramid edges R = 2 mu^2 (1 + mu^2) (w_a + w_b) (1-imp)/imp    */
+#endif
+#ifndef ORC_PT_CONTACT_MIDPOINT /* 0: contact point on the box surface instead of midway between the two surfaces */
+#define ORC_PT_CONTACT_MIDPOINT 1
+#endif
+
 static inline float pt_clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 /* impedance and reference acceleration of one constraint row (MuJoCo solver parameters, power = 2) */
@@ -113,7 +122,7 @@ static void pt_substep(const float* P, float* q, float* qd, const float* u) {
       else { nlx = 0.0f; nly = ly < 0.0f ? -1.0f : 1.0f; dist = (0.0f - py) - rp; sy = nly * B[3]; }
     }
     const float nx = c * nlx - s * nly, ny = s * nlx + c * nly;
-    const float half = 0.5f * dist;
+    const float half = ORC_PT_CONTACT_MIDPOINT ? 0.5f * dist : 0.0f;
     const float ax = B[0] + (sx + nlx * half), ay = B[1] + (sy + nly * half); /* contact point, body frame */
     const float rhox = c * ax - s * ay, rhoy = s * ax + c * ay;                /* arm from the slider origin */
     const float tx = 0.0f - ny, ty = nx;
@@ -173,7 +182,20 @@ static void pt_substep(const float* P, float* q, float* qd, const float* u) {
         float imp, aref;
         pt_imp_aref(P, R.pos[idx[i]], vel, &imp, &aref);
         const float arr = A[i][i];
+#if ORC_PT_REG_INVWEIGHT
+        {
+          /* translational inverse weights at qpos0 (MuJoCo body_invweight0: trace(J M^-1 J^T) / 3 at the body COM, the z direction
+           * has no dof) and dof inverse weights (diagonal of M^-1 at qpos0) */
+          const float wp = (2.0f * P[MBD_PT_IMP]) / 3.0f, ws = (2.0f * ims) / 3.0f;
+          const int r = idx[i];
+          float wr;
+          if (r < MBD_PT_NLIM) wr = r < 2 ? P[MBD_PT_IMP] : (r == 2 ? ims + (P[MBD_PT_CY] * P[MBD_PT_CY]) * iIs : ims + (P[MBD_PT_CX] * P[MBD_PT_CX]) * iIs);
+          else wr = 2.0f * (mu * mu) * ((1.0f + mu * mu) * (wp + ws));
+          A[i][i] = arr + (R.rscale[r] * ((1.0f - imp) / imp)) * wr;
+        }
+#else
         A[i][i] = arr + (R.rscale[idx[i]] * ((1.0f - imp) / imp)) * arr;
+#endif
         invD[i] = 1.0f / A[i][i];
         bq[i] = ((((J[0] * Mif[0] + J[1] * Mif[1]) + J[2] * Mif[2]) + J[3] * Mif[3]) + J[4] * Mif[4]) - aref;
       } else {

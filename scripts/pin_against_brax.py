@@ -50,6 +50,7 @@ SWITCHES = {  # name -> candidate values (first = the default the CUDA kernels i
     "ORC_EULER_ACOS": [0, 1],
     "ORC_EPS": ["1e-6f", "0.0f"],
 }
+PT_SWITCHES = {"ORC_PT_REG_INVWEIGHT": [0, 1], "ORC_PT_CONTACT_MIDPOINT": [1, 0]}   # oracle/pusht_oracle.c
 FIELDS = [("x_i.pos", slice(0, 3)), ("x_i.rot", slice(3, 7)), ("xd_i.ang", slice(7, 10)), ("xd_i.vel", slice(10, 13))]
 
 
@@ -101,11 +102,27 @@ def compare(dump_path: str, limit: int = 0):
         from oracle import oracle as orc
         pt = mbd_b200.envs.get_env("pushT")
         x0 = np.concatenate([np.float32(d["pusht_q0"]), np.zeros(8, np.float32)])
-        mine = orc.pusht_rollout(pt.params, x0, np.float32(d["pusht_actions"])[None], want_traj=True)["traj"][0]
-        err = np.abs(mine - np.float32(d["pusht_traj"]))
-        print(f"  max |q diff| = {err[:, :8].max():.3e}   max |qd diff| = {err[:, 8:].max():.3e}   (first env step: {err[0].max():.3e})")
-        print("  " + ("PINNED to 1e-3" if err.max() < 1e-3 else "NOT PINNED: the two declared own choices (solver, regulariser diagonal) or a "
-                                                          "[brax-recalled] item of oracle/pusht_oracle.c differ — see its header"))
+        acts = np.float32(d["pusht_actions"])[None]
+        ref = np.float32(d["pusht_traj"])
+        pt_rows = []
+        with tempfile.TemporaryDirectory() as tmp:
+            for ci, combo in enumerate(itertools.product(*PT_SWITCHES.values())):
+                defs = dict(zip(PT_SWITCHES, combo))
+                lib = build_variant(defs, os.path.join(tmp, f"pt{ci}.so"))
+                old, orc._LIB = orc._LIB, lib
+                try:
+                    mine = orc.pusht_rollout(pt.params, x0, acts, want_traj=True, nthreads=1)["traj"][0]
+                finally:
+                    orc._LIB = old
+                err = np.abs(mine - ref)
+                pt_rows.append((float(err.max()), float(err[0].max()), defs))
+        pt_rows.sort(key=lambda r: r[0])
+        pt_default = {n: v[0] for n, v in PT_SWITCHES.items()}
+        for tot, first, defs in pt_rows:
+            tag = "DEFAULT (what the kernel implements)" if defs == pt_default else ", ".join(f"{k}={v}" for k, v in defs.items() if v != pt_default[k])
+            print(f"  max |q, qd diff| = {tot:.3e}   after the first env step {first:.3e}   [{tag}]")
+        print("  " + ("PINNED to 1e-3" if pt_rows[0][0] < 1e-3 else "NOT PINNED: the declared own choices (solver, regulariser diagonal, merged pyramid pair) or a "
+                                                               "[brax-recalled] item of oracle/pusht_oracle.c differ — see its header"))
     print("== (3) positional step, stage by stage, from the dump's own states ==")
     states, action = np.float32(d["states"]), np.float32(d["action"])     # [K+1, L, 13], [Nu]
     names = list(SWITCHES)
